@@ -1,0 +1,317 @@
+// 2-D convolution (k in {1,3}, stride 1, zero pad k/2) as a tcgen05 implicit GEMM for sm_100a.
+//
+//   reference call site: F.conv2d in DOConv2d._conv_forward (p2igan_bench/modules/deconv_pytorch.py:104-109)
+//   with the ReLU / residual of BasicConv_do / ResBlock_do fused (p2igan_bench/modules/layer.py:84-94,134-135),
+//   and the 1x1 projection of UPPos (layer.py:390,398).
+//
+// GEMM view: M = B*H*W output pixels, N = Cout, K = k*k*Cin.
+//   A (activations) : NHWC bf16. One CTA tile = Ht x Wt = 128 output pixels of one image. For every
+//       64-channel block and every horizontal tap kx ONE TMA box of (Ht+k-1) x Wt pixels x 64 channels is
+//       loaded (out-of-image pixels are zero-filled by the TMA unit = the conv's zero padding). The k
+//       vertical taps reuse that box: tap ky starts ky*Wt rows further down, which is a multiple of
+//       1024 B because Wt % 8 == 0, so every shifted view is still a valid 128B-swizzled K-major
+//       UMMA operand. A is therefore fetched k (not k*k) times.
+//   B (weights)     : bf16 [tap][Cout][Cin] (K-major), one TMA box of NT x 64 per (tap, channel block).
+//   D (accumulator) : fp32 in TMEM, 128 lanes x NT columns, double buffered (2*NT <= 512 columns) so the
+//       epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (256 threads, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer (one elected
+// thread), warp2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> regs -> residual/ReLU -> bf16 -> global).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace p2i {
+
+struct ConvParams {
+    int B, H, W, Cin, Cout;
+    int KH, KW;
+    int Ht, Wt;
+    int tiles_x, tiles_y, m_tiles, total_tiles;
+    int relu;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* y;
+};
+
+template <int NT>
+struct ConvCfg {
+    static constexpr int SA = 3;
+    static constexpr int SB = (NT == 256) ? 4 : (NT == 128 ? 6 : 8);
+    static constexpr int A_STAGE = 20480;  // max over tile shapes: (8+2)*16*128 B
+    static constexpr int B_STAGE = NT * 128;
+    static constexpr int NBAR = 2 * SA + 2 * SB + 4;
+    static constexpr int SMEM = 1024 + SA * A_STAGE + SB * B_STAGE + NBAR * 8 + 16;
+    static constexpr int TMEM_COLS = 2 * NT;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+    using Cfg = ConvCfg<NT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + Cfg::SA * Cfg::A_STAGE;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + Cfg::SB * Cfg::B_STAGE);
+    uint64_t* emptyA = fullA + Cfg::SA;
+    uint64_t* fullB = emptyA + Cfg::SA;
+    uint64_t* emptyB = fullB + Cfg::SB;
+    uint64_t* tfull = emptyB + Cfg::SB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < Cfg::SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cblocks = p.Cin >> 6;
+    const uint32_t a_bytes = static_cast<uint32_t>((p.Ht + p.KH - 1) * p.Wt * 128);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ---------------------------------------------------------------- TMA producer
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+                const int b = mt / tiles_per_img, r = mt - b * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * p.Ht, x0 = (r % p.tiles_x) * p.Wt;
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    for (int kx = 0; kx < p.KW; ++kx) {
+                        mbar_wait(&emptyA[sa], pa ^ 1);
+                        mbar_expect_tx(&fullA[sa], a_bytes);
+                        tma_load_4d(sA + sa * Cfg::A_STAGE, &tmA, &fullA[sa], cb * 64, x0 + kx - (p.KW >> 1),
+                                    y0 - (p.KH >> 1), b);
+                        if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
+                        for (int ky = 0; ky < p.KH; ++ky) {
+                            mbar_wait(&emptyB[sb], pb ^ 1);
+                            mbar_expect_tx(&fullB[sb], Cfg::B_STAGE);
+                            tma_load_3d(sB + sb * Cfg::B_STAGE, &tmB, &fullB[sb], cb * 64, nt * NT, ky * p.KW + kx);
+                            if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ---------------------------------------------------------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * NT;
+                uint32_t acc = 0;
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    for (int kx = 0; kx < p.KW; ++kx) {
+                        mbar_wait(&fullA[sa], pa);
+                        const uint32_t a_base = smem_u32(sA + sa * Cfg::A_STAGE);
+                        for (int ky = 0; ky < p.KH; ++ky) {
+                            mbar_wait(&fullB[sb], pb);
+                            tc_fence_after();
+                            const uint32_t a_addr = a_base + ky * p.Wt * 128;
+                            const uint32_t b_addr = smem_u32(sB + sb * Cfg::B_STAGE);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024),
+                                          make_sw128_desc(b_addr + k * 32, 16, 1024), idesc, acc);
+                                acc = 1;
+                            }
+                            umma_commit(&emptyB[sb]);
+                            if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                        }
+                        umma_commit(&emptyA[sa]);
+                        if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // -------------------------------------------------------------------- epilogue
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            const int b = mt / tiles_per_img, r = mt - b * tiles_per_img;
+            const int y = (r / p.tiles_x) * p.Ht + row / p.Wt;
+            const int x = (r % p.tiles_x) * p.Wt + row % p.Wt;
+            const bool valid = (y < p.H) && (x < p.W);
+            const size_t off = ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.Cout + nt * NT;
+            mbar_wait(&tfull[as], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + as * NT + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < NT; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + c, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.residual != nullptr) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+                        uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float2 t = unpack_bf16x2(rr[i]);
+                            f[2 * i] += t.x;
+                            f[2 * i + 1] += t.y;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    uint4* op = reinterpret_cast<uint4*>(p.y + off + c);
+                    op[0] = o0;
+                    op[1] = o1;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int NT>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+    using Cfg = ConvCfg<NT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM);
+        if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_igemm smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_igemm_kernel<NT><<<grid, 256, Cfg::SMEM, st>>>(tmA, tmB, p);
+    P2I_CHECK_LAUNCH("conv_igemm_kernel");
+    return P2I_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// CUDA-core direct convolution: same contract, used by tests to triage the tensor-core kernel.
+// --------------------------------------------------------------------------------------------
+__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                   const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, int B, int H,
+                                   int W, int Cin, int Cout, int K, int relu) {
+    const long long total = static_cast<long long>(B) * H * W * Cout;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Cout);
+        long long pix = i / Cout;
+        const int xx = static_cast<int>(pix % W);
+        const int yy = static_cast<int>((pix / W) % H);
+        const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        float acc = 0.f;
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = yy + ky - K / 2;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = xx + kx - K / 2;
+                if (ix < 0 || ix >= W) continue;
+                const __nv_bfloat16* xp = x + ((static_cast<size_t>(b) * H + iy) * W + ix) * Cin;
+                const __nv_bfloat16* wp = w + (static_cast<size_t>(ky * K + kx) * Cout + co) * Cin;
+                for (int ci = 0; ci < Cin; ++ci) acc += __bfloat162float(xp[ci]) * __bfloat162float(wp[ci]);
+            }
+        }
+        if (res) acc += __bfloat162float(res[i]);
+        if (relu) acc = fmaxf(acc, 0.f);
+        y[i] = __float2bfloat16(acc);
+    }
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W,
+                                    int Cin, int Cout, int ksize, int flags, void* stream) {
+    P2I_CHECK_ARG(x && w && y, "conv2d_igemm: null pointer");
+    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_igemm: ksize %d unsupported (1 or 3)", ksize);
+    P2I_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape B=%d H=%d W=%d", B, H, W);
+    P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+                  "conv2d_igemm: Cin=%d Cout=%d must be positive multiples of 64", Cin, Cout);
+    ConvParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.KH = ksize; p.KW = ksize;
+    p.Wt = (W >= 16) ? 16 : 8;
+    p.Ht = 128 / p.Wt;
+    p.tiles_x = cdiv(W, p.Wt);
+    p.tiles_y = cdiv(H, p.Ht);
+    p.m_tiles = B * p.tiles_x * p.tiles_y;
+    p.relu = (flags & P2I_CONV_RELU) ? 1 : 0;
+    p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.y = static_cast<__nv_bfloat16*>(y);
+    const int NT = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+    p.total_tiles = p.m_tiles * (Cout / NT);
+
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
+        const uint64_t strides[4] = {0, uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
+        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht + ksize - 1), 1};
+        int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr, true);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[3] = {uint64_t(Cin), uint64_t(Cout), uint64_t(ksize * ksize)};
+        const uint64_t strides[3] = {0, uint64_t(Cin) * 2, uint64_t(Cout) * Cin * 2};
+        const uint32_t box[3] = {64, uint32_t(NT), 1};
+        int rc = encode_tmap_bf16(&tmB, w, 3, dims, strides, box, nullptr, true);
+        if (rc) return rc;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (NT == 256) return launch_conv<256>(tmA, tmB, p, st);
+    if (NT == 128) return launch_conv<128>(tmA, tmB, p, st);
+    return launch_conv<64>(tmA, tmB, p, st);
+}
+
+extern "C" int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W,
+                                     int Cin, int Cout, int ksize, int flags, void* stream) {
+    P2I_CHECK_ARG(x && w && y, "conv2d_direct: null pointer");
+    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_direct: ksize %d unsupported", ksize);
+    const long long total = static_cast<long long>(B) * H * W * Cout;
+    int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    conv_direct_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
+        static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), B, H, W, Cin, Cout, ksize,
+        (flags & P2I_CONV_RELU) ? 1 : 0);
+    P2I_CHECK_LAUNCH("conv_direct_kernel");
+    return P2I_OK;
+}

@@ -1,0 +1,80 @@
+// DO-Conv weight composition (p2igan_bench/modules/deconv_pytorch.py:111-132):
+//   DoW[o,i,m] = sum_s (D + D_diag)[i,m,s] * W[o,i,s]        (groups = 1, 3x3: m,s in 0..8)
+// written straight into the bf16 operand layouts of the implicit-GEMM kernels:
+//   out   [m][o][i]            forward B operand (K = input channels contiguous)
+//   out_t [8-m][i][o]          dgrad   B operand (taps flipped, K = output channels contiguous)
+// One launch covers a whole table of layers (33 tiny einsum launches in the reference).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace p2i {
+
+// block = (32 input channels) x (8 output-channel lanes); grid = (C/32, C/64, layer)
+__global__ void __launch_bounds__(256) doconv_compose_kernel(const P2iDoLayer* __restrict__ table) {
+    const P2iDoLayer L = table[blockIdx.z];
+    const int C = L.channels;
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+    if (i0 >= C || o0 >= C) return;
+    __shared__ float sD[32][82];  // (D + D_diag)[i0 + ii][m*9 + s], padded against bank conflicts
+    for (int e = threadIdx.x; e < 32 * 81; e += 256) {
+        const int ii = e / 81, r = e - ii * 81;
+        const size_t g = static_cast<size_t>(i0 + ii) * 81 + r;
+        sD[ii][r] = L.D[g] + L.D_diag[g];
+    }
+    __syncthreads();
+    const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
+    const int i = i0 + ii;
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(L.out);
+    __nv_bfloat16* out_t = static_cast<__nv_bfloat16*>(L.out_t);
+    for (int o = o0 + oo; o < o0 + 64; o += 8) {
+        const float* wp = L.W + (static_cast<size_t>(o) * C + i) * 9;
+        float w[9];
+#pragma unroll
+        for (int s = 0; s < 9; ++s) w[s] = wp[s];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) acc = fmaf(sD[ii][m * 9 + s], w[s], acc);
+            const __nv_bfloat16 v = __float2bfloat16(acc);
+            out[(static_cast<size_t>(m) * C + o) * C + i] = v;
+            if (out_t) out_t[(static_cast<size_t>(8 - m) * C + i) * C + o] = v;
+        }
+    }
+}
+
+// Convsin: W [64,4,9] is raw-reshaped to [16,16,9] before the einsum (deconv_pytorch.py:119), which pairs
+// weight row (oc, icl) with D row i = (oc % 4) * 4 + icl.  out f32 [64][4][9].
+__global__ void doconv_compose_stem_kernel(const float* __restrict__ W, const float* __restrict__ D,
+                                           const float* __restrict__ Dd, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (oc, icl, m)
+    if (idx >= 64 * 4 * 9) return;
+    const int m = idx % 9, icl = (idx / 9) % 4, oc = idx / 36;
+    const int i = (oc % 4) * 4 + icl;
+    const float* wp = W + (oc * 4 + icl) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < 9; ++s) acc = fmaf(D[(i * 9 + m) * 9 + s] + Dd[(i * 9 + m) * 9 + s], wp[s], acc);
+    out[idx] = acc;
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_doconv_compose_fwd(const P2iDoLayer* table_dev, int n_layers, int max_channels, void* stream) {
+    P2I_CHECK_ARG(table_dev && n_layers > 0, "doconv_compose: empty table");
+    P2I_CHECK_ARG(max_channels % 64 == 0 && max_channels > 0, "doconv_compose: channels must be a multiple of 64");
+    dim3 grid(max_channels / 32, max_channels / 64, n_layers);
+    doconv_compose_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
+    P2I_CHECK_LAUNCH("doconv_compose_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_doconv_compose_stem_fwd(const float* W, const float* D, const float* D_diag, float* out,
+                                           void* stream) {
+    P2I_CHECK_ARG(W && D && D_diag && out, "doconv_compose_stem: null pointer");
+    doconv_compose_stem_kernel<<<cdiv(64 * 4 * 9, 256), 256, 0, as_stream(stream)>>>(W, D, D_diag, out);
+    P2I_CHECK_LAUNCH("doconv_compose_stem_kernel");
+    return P2I_OK;
+}

@@ -1,0 +1,437 @@
+// InputBlock of the generator: ordered point extraction, per-point gating and 4-NN inverse-distance
+// interpolation (p2igan_bench/modules/layer.py:246-361).  All CUDA-core work; the search is integer-exact.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace p2i {
+
+// ------------------------------------------------------------------------------------------------
+// torch.nonzero(mask > 0) per sample in (t,y,x) order (layer.py:329): ordered stream compaction.
+// One block per sample; each round compacts 4096 elements with ballot + block scan.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) points_extract_kernel(const float* __restrict__ masks, int Q, int* __restrict__ pts,
+                                                               int* __restrict__ counts, int cap) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_s, round_tot;
+    const int b = blockIdx.x;
+    const float* m = masks + static_cast<size_t>(b) * Q;
+    int* out = pts + static_cast<size_t>(b) * cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int start = 0; start < Q; start += 4096) {
+        const int i0 = start + threadIdx.x * 4;
+        int flags = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < Q && m[i0 + j] > 0.f) flags |= 1 << j;
+        const int cnt = __popc(flags);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = warp_tot[lane];
+            int s = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += u;
+            }
+            warp_tot[lane] = s - v;  // exclusive prefix of warp totals
+            if (lane == 31) round_tot = s;
+        }
+        __syncthreads();
+        int pos = base_s + warp_tot[warp] + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (flags & (1 << j)) {
+                if (pos < cap) out[pos] = i0 + j;
+                ++pos;
+            }
+        __syncthreads();
+        if (threadIdx.x == 0) base_s += round_tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[b] = base_s < cap ? base_s : cap;
+}
+
+// src[b] = 0 when sample b observes exactly the same points as sample 0 (the 'stis' gauge mask is
+// one pattern for the whole batch, sti_dataset.py:104-117), else b.  Lets the kNN search run once.
+__global__ void points_dedup_kernel(const int* __restrict__ pts, const int* __restrict__ counts, int cap,
+                                    int* __restrict__ src) {
+    __shared__ int differ;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) differ = 0;
+    __syncthreads();
+    const int n = counts[b];
+    if (n != counts[0]) {
+        if (threadIdx.x == 0) differ = 1;
+    } else {
+        const int* a = pts;
+        const int* c = pts + static_cast<size_t>(b) * cap;
+        int d = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d |= (a[i] != c[i]);
+        if (d) differ = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) src[b] = differ ? b : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionBlock x2 at observed points only (layer.py:296-304, 318-322, 344).
+// ------------------------------------------------------------------------------------------------
+__global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const int* __restrict__ pts,
+                                       const int* __restrict__ counts, int cap, const float* __restrict__ w0,
+                                       const float* __restrict__ b0, const float* __restrict__ w1,
+                                       const float* __restrict__ b1, float* __restrict__ vals,
+                                       float* __restrict__ gate_l1, int HW) {
+    __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; }
+    if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[b]) return;
+    const int p = pts[static_cast<size_t>(b) * cap + i];
+    const int t = p / HW, pix = p - t * HW;
+    const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
+    float x[16], h[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = xin[static_cast<size_t>(k) * HW];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float g = sb0[j];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) g = fmaf(sw0[j * 16 + k], x[k], g);
+        h[j] = fmaxf(fmaf(x[j], g, x[j]), 0.f);
+    }
+    float g = sb1[t];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g = fmaf(sw1[t * 16 + k], h[k], g);
+    float ht = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ht = (k == t) ? h[k] : ht;
+    vals[static_cast<size_t>(b) * cap + i] = fmaxf(fmaf(ht, g, ht), 0.f);
+    if (gate_l1) {
+        float* o = gate_l1 + (static_cast<size_t>(b) * cap + i) * 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o[k] = h[k];
+    }
+}
+
+// Backward of the two gates for the single output channel t that feeds `vals`.
+__global__ void gate_points_bwd_kernel(const float* __restrict__ masked, const int* __restrict__ pts,
+                                       const int* __restrict__ counts, int cap, const float* __restrict__ w0,
+                                       const float* __restrict__ b0, const float* __restrict__ w1,
+                                       const float* __restrict__ b1, const float* __restrict__ dvals,
+                                       float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
+                                       float* __restrict__ db1, int HW) {
+    __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
+    __shared__ float aw0[256], aw1[256], ab0[16], ab1[16];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; aw0[i] = 0.f; aw1[i] = 0.f; }
+    if (threadIdx.x < 16) {
+        sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x];
+        ab0[threadIdx.x] = 0.f; ab1[threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < counts[b]) {
+        const int p = pts[static_cast<size_t>(b) * cap + i];
+        const int t = p / HW, pix = p - t * HW;
+        const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
+        float x[16], h[16], g0[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = xin[static_cast<size_t>(k) * HW];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float g = sb0[j];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g = fmaf(sw0[j * 16 + k], x[k], g);
+            g0[j] = g;
+            h[j] = fmaxf(fmaf(x[j], g, x[j]), 0.f);
+        }
+        float g1 = sb1[t];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) g1 = fmaf(sw1[t * 16 + k], h[k], g1);
+        float ht = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ht = (k == t) ? h[k] : ht;
+        const float pre = fmaf(ht, g1, ht);
+        float dv = dvals[static_cast<size_t>(b) * cap + i];
+        if (pre <= 0.f) dv = 0.f;
+        if (dv != 0.f) {
+            // v = ht*(1+g1):  d g1 = dv*ht ; d ht += dv*(1+g1) ; g1 = b1[t] + sum_k w1[t,k] h[k]
+            const float dg1 = dv * ht;
+            atomicAdd(&ab1[t], dg1);
+            float dh[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                atomicAdd(&aw1[t * 16 + k], dg1 * h[k]);
+                dh[k] = dg1 * sw1[t * 16 + k] + ((k == t) ? dv * (1.f + g1) : 0.f);
+            }
+            // h[j] = relu(x[j]*(1+g0[j])) : d g0[j] = dh[j]*x[j] when active
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (h[j] > 0.f && dh[j] != 0.f) {
+                    const float dg0 = dh[j] * x[j];
+                    if (dg0 != 0.f) {
+                        atomicAdd(&ab0[j], dg0);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (x[k] != 0.f) atomicAdd(&aw0[j * 16 + k], dg0 * x[k]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        if (aw0[k] != 0.f) atomicAdd(&dw0[k], aw0[k]);
+        if (aw1[k] != 0.f) atomicAdd(&dw1[k], aw1[k]);
+    }
+    if (threadIdx.x < 16) {
+        if (ab0[threadIdx.x] != 0.f) atomicAdd(&db0[threadIdx.x], ab0[threadIdx.x]);
+        if (ab1[threadIdx.x] != 0.f) atomicAdd(&db1[threadIdx.x], ab1[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4-NN search (layer.py:280-281) with exact integer keys.
+//   key = cx*dx^2 + cy*dy^2 + cz*dt^2  (common-denominator form of the squared normalised distance)
+//   order = (key, point index): ties go to the smaller index (the order torch.nonzero yields).
+// Frames are visited by increasing |dt| and a frame is skipped as soon as cz*dt^2 alone reaches the
+// current 4th best, so with one gauge pattern on every frame only ~3-5 of the 16 frames are scanned.
+// ------------------------------------------------------------------------------------------------
+constexpr int IDW_SMEM_PTS = 8192;
+
+struct IdwGeom {
+    int T, H, W;
+    unsigned cx, cy, cz;     // integer key coefficients (gcd removed)
+    float fx, fy, fz;        // 1/(W-1)^2, 1/(H-1)^2, 1/(T-1)^2
+    float tau;
+};
+
+__device__ __forceinline__ void top4_insert(unsigned long long c, unsigned long long (&best)[4]) {
+    if (c < best[3]) {
+        best[3] = c;
+        if (best[3] < best[2]) { unsigned long long t = best[2]; best[2] = best[3]; best[3] = t; }
+        if (best[2] < best[1]) { unsigned long long t = best[1]; best[1] = best[2]; best[2] = t; }
+        if (best[1] < best[0]) { unsigned long long t = best[0]; best[0] = best[1]; best[1] = t; }
+    }
+}
+
+__global__ void __launch_bounds__(256) idw_search_kernel(const int* __restrict__ pts, const int* __restrict__ counts,
+                                                         const int* __restrict__ src, int cap, int* __restrict__ nbr_idx,
+                                                         float* __restrict__ nbr_w, IdwGeom g) {
+    __shared__ unsigned s_yx[IDW_SMEM_PTS];
+    __shared__ int s_fs[260];
+    const int b = blockIdx.y;
+    if (src && src[b] != b) return;  // neighbour table shared with sample src[b]
+    const int HW = g.H * g.W, Q = g.T * HW;
+    const int N = counts[b];
+    const int* P = pts + static_cast<size_t>(b) * cap;
+    // frame segment boundaries by binary search: first index with p >= f*HW
+    for (int f = threadIdx.x; f <= g.T; f += blockDim.x) {
+        int lo = 0, hi = N;
+        const int target = f * HW;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (P[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        s_fs[f] = lo;
+    }
+    const bool in_smem = N <= IDW_SMEM_PTS;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int p = P[i];
+            const int pix = p % HW;
+            s_yx[i] = (static_cast<unsigned>(pix / g.W) << 16) | static_cast<unsigned>(pix % g.W);
+        }
+    }
+    __syncthreads();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = q < Q;
+    const int qq = active ? q : Q - 1;
+    const int qt = qq / HW, qpix = qq - qt * HW, qy = qpix / g.W, qx = qpix - qy * g.W;
+    unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    for (int off = 0; off < g.T; ++off) {
+        const unsigned kt = g.cz * static_cast<unsigned>(off * off);
+        const bool dead = (static_cast<unsigned long long>(kt) << 22) >= best[3];
+        if (__all_sync(0xffffffffu, dead)) break;
+        for (int sgn = 0; sgn < (off == 0 ? 1 : 2); ++sgn) {
+            const int f = sgn == 0 ? qt - off : qt + off;
+            // warp-uniform bounds are not guaranteed (a block can straddle two frames), so predicate per thread
+            const bool use = !dead && f >= 0 && f < g.T;
+            const int fcl = f < 0 ? 0 : (f >= g.T ? g.T - 1 : f);
+            const int s0 = s_fs[fcl], s1 = s_fs[fcl + 1];
+            if (__all_sync(0xffffffffu, !use)) continue;
+            for (int i = s0; i < s1; ++i) {
+                unsigned yx;
+                if (in_smem) yx = s_yx[i];
+                else {
+                    const int pix = __ldg(P + i) % HW;
+                    yx = (static_cast<unsigned>(pix / g.W) << 16) | static_cast<unsigned>(pix % g.W);
+                }
+                const int dy = qy - static_cast<int>(yx >> 16), dx = qx - static_cast<int>(yx & 0xffffu);
+                const unsigned key = g.cx * static_cast<unsigned>(dx * dx) + g.cy * static_cast<unsigned>(dy * dy) + kt;
+                const unsigned long long c = (static_cast<unsigned long long>(key) << 22) | static_cast<unsigned>(i);
+                if (use) top4_insert(c, best);
+            }
+        }
+    }
+    if (!active) return;
+    float w[4];
+    int id[4];
+    float wsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (best[j] == ~0ull) { w[j] = 0.f; id[j] = 0; continue; }
+        id[j] = static_cast<int>(best[j] & ((1u << 22) - 1));
+        const int p = __ldg(P + id[j]);
+        const int pt = p / HW, pix = p - pt * HW, py = pix / g.W, px = pix - py * g.W;
+        const float dx = static_cast<float>(qx - px), dy = static_cast<float>(qy - py), dt = static_cast<float>(qt - pt);
+        const float d = sqrtf(g.fx * dx * dx + g.fy * dy * dy + g.fz * dt * dt);
+        const float inv = 1.f / (d + g.tau);
+        w[j] = inv * inv;
+        wsum += w[j];
+    }
+    const float norm = 1.f / (wsum + 1e-12f);
+    const size_t o = (static_cast<size_t>(b) * Q + q) * 4;
+    *reinterpret_cast<int4*>(nbr_idx + o) = make_int4(id[0], id[1], id[2], id[3]);
+    *reinterpret_cast<float4*>(nbr_w + o) = make_float4(w[0] * norm, w[1] * norm, w[2] * norm, w[3] * norm);
+}
+
+__global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* __restrict__ nbr_w,
+                                  const float* __restrict__ vals, const int* __restrict__ counts,
+                                  const int* __restrict__ src, int cap, float* __restrict__ out, int Q) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    float r = 0.f;
+    if (counts[b] > 0) {
+        const int sb = src ? src[b] : b;
+        const size_t o = (static_cast<size_t>(sb) * Q + q) * 4;
+        const int4 id = __ldg(reinterpret_cast<const int4*>(nbr_idx + o));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(nbr_w + o));
+        const float* v = vals + static_cast<size_t>(b) * cap;
+        r = w.x * __ldg(v + id.x) + w.y * __ldg(v + id.y) + w.z * __ldg(v + id.z) + w.w * __ldg(v + id.w);
+    }
+    out[static_cast<size_t>(b) * Q + q] = r;
+}
+
+__global__ void idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
+                                      const float* __restrict__ nbr_w, const int* __restrict__ counts,
+                                      const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q || counts[b] == 0) return;
+    const float g = dout[static_cast<size_t>(b) * Q + q];
+    if (g == 0.f) return;
+    const int sb = src ? src[b] : b;
+    const size_t o = (static_cast<size_t>(sb) * Q + q) * 4;
+    const int4 id = __ldg(reinterpret_cast<const int4*>(nbr_idx + o));
+    const float4 w = __ldg(reinterpret_cast<const float4*>(nbr_w + o));
+    float* v = dvals + static_cast<size_t>(b) * cap;
+    if (w.x != 0.f) atomicAdd(v + id.x, w.x * g);
+    if (w.y != 0.f) atomicAdd(v + id.y, w.y * g);
+    if (w.z != 0.f) atomicAdd(v + id.z, w.z * g);
+    if (w.w != 0.f) atomicAdd(v + id.w, w.w * g);
+}
+
+static unsigned long long gcd_ull(unsigned long long a, unsigned long long b) {
+    while (b) { unsigned long long t = a % b; a = b; b = t; }
+    return a;
+}
+
+static int make_geom(int T, int H, int W, float tau, IdwGeom* g) {
+    const unsigned long long sw = W > 1 ? W - 1 : 1, sh = H > 1 ? H - 1 : 1, sd = T > 1 ? T - 1 : 1;
+    unsigned long long cx = (sh * sd) * (sh * sd), cy = (sw * sd) * (sw * sd), cz = (sw * sh) * (sw * sh);
+    const unsigned long long gg = gcd_ull(gcd_ull(cx, cy), cz);
+    cx /= gg; cy /= gg; cz /= gg;
+    const unsigned long long maxkey = cx * sw * sw + cy * sh * sh + cz * sd * sd;
+    if (maxkey >= (1ull << 32)) return fail(P2I_ERR_INVALID, "idw: grid %dx%dx%d needs >32-bit distance keys", T, H, W);
+    if (static_cast<long long>(T) * H * W >= (1ll << 22))
+        return fail(P2I_ERR_INVALID, "idw: T*H*W=%lld exceeds 2^22 points", static_cast<long long>(T) * H * W);
+    g->T = T; g->H = H; g->W = W;
+    g->cx = static_cast<unsigned>(cx); g->cy = static_cast<unsigned>(cy); g->cz = static_cast<unsigned>(cz);
+    g->fx = 1.f / static_cast<float>(sw * sw);
+    g->fy = 1.f / static_cast<float>(sh * sh);
+    g->fz = 1.f / static_cast<float>(sd * sd);
+    g->tau = tau;
+    return P2I_OK;
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_points_extract(const float* masks, int B, int T, int H, int W, int* pts, int* counts, int* src,
+                                  int cap, void* stream) {
+    P2I_CHECK_ARG(masks && pts && counts, "points_extract: null pointer");
+    P2I_CHECK_ARG(B > 0 && T > 0 && H > 0 && W > 0 && cap > 0, "points_extract: bad shape");
+    points_extract_kernel<<<B, 1024, 0, as_stream(stream)>>>(masks, T * H * W, pts, counts, cap);
+    P2I_CHECK_LAUNCH("points_extract_kernel");
+    if (src) {
+        points_dedup_kernel<<<B, 256, 0, as_stream(stream)>>>(pts, counts, cap, src);
+        P2I_CHECK_LAUNCH("points_dedup_kernel");
+    }
+    return P2I_OK;
+}
+
+extern "C" int p2i_gate_points_fwd(const float* masked, const int* pts, const int* counts, int cap, const float* w0,
+                                   const float* b0, const float* w1, const float* b1, float* vals, float* gate_l1,
+                                   int B, int T, int H, int W, void* stream) {
+    P2I_CHECK_ARG(T == 16, "gate_points: the reference hard-wires 16 frames (layer.py:310), got T=%d", T);
+    P2I_CHECK_ARG(masked && pts && counts && w0 && b0 && w1 && b1 && vals, "gate_points: null pointer");
+    dim3 grid(cdiv(cap, 128), B);
+    gate_points_fwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(masked, pts, counts, cap, w0, b0, w1, b1, vals, gate_l1,
+                                                                H * W);
+    P2I_CHECK_LAUNCH("gate_points_fwd_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_gate_points_bwd(const float* masked, const int* pts, const int* counts, int cap, const float* w0,
+                                   const float* b0, const float* w1, const float* b1, const float* dvals, float* dw0,
+                                   float* db0, float* dw1, float* db1, int B, int T, int H, int W, void* stream) {
+    P2I_CHECK_ARG(T == 16, "gate_points_bwd: T must be 16, got %d", T);
+    P2I_CHECK_ARG(masked && pts && counts && dvals && dw0 && db0 && dw1 && db1, "gate_points_bwd: null pointer");
+    dim3 grid(cdiv(cap, 128), B);
+    gate_points_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(masked, pts, counts, cap, w0, b0, w1, b1, dvals, dw0, db0,
+                                                                dw1, db1, H * W);
+    P2I_CHECK_LAUNCH("gate_points_bwd_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_idw_knn_fwd(const int* pts, const float* vals, const int* counts, const int* src, int cap, float* out,
+                               int* nbr_idx, float* nbr_w, int B, int T, int H, int W, float tau, int search,
+                               void* stream) {
+    P2I_CHECK_ARG(pts && vals && counts && out && nbr_idx && nbr_w, "idw_knn_fwd: null pointer");
+    IdwGeom g;
+    int rc = make_geom(T, H, W, tau, &g);
+    if (rc) return rc;
+    const int Q = T * H * W;
+    dim3 grid(cdiv(Q, 256), B);
+    if (search) {
+        idw_search_kernel<<<grid, 256, 0, as_stream(stream)>>>(pts, counts, src, cap, nbr_idx, nbr_w, g);
+        P2I_CHECK_LAUNCH("idw_search_kernel");
+    }
+    idw_interp_kernel<<<grid, 256, 0, as_stream(stream)>>>(nbr_idx, nbr_w, vals, counts, src, cap, out, Q);
+    P2I_CHECK_LAUNCH("idw_interp_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const float* nbr_w, const int* counts,
+                               const int* src, float* dvals, int cap, int B, int T, int H, int W, void* stream) {
+    P2I_CHECK_ARG(dout && nbr_idx && nbr_w && counts && dvals, "idw_knn_bwd: null pointer");
+    const int Q = T * H * W;
+    dim3 grid(cdiv(Q, 256), B);
+    idw_interp_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, nbr_idx, nbr_w, counts, src, cap, dvals, Q);
+    P2I_CHECK_LAUNCH("idw_interp_bwd_kernel");
+    return P2I_OK;
+}

@@ -1,0 +1,157 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point of include/p2i_b200.h).
+
+Tensors are PyTorch-owned device memory; PyTorch supplies the allocator and the current stream only.
+"cl" = channels-last activations, shape [B, H, W, C], bf16, contiguous.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import LIB, ptr, require_cuda, stream
+
+Tensor = torch.Tensor
+
+
+def _chk(t: Tensor, dtype, name: str) -> Tensor:
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------- InputBlock
+def points_extract(masks: Tensor, cap: Optional[int] = None):
+    """masks [B,T,H,W] f32 -> (pts [B,cap] i32, counts [B] i32, src [B] i32)."""
+    require_cuda(masks)
+    B, T, H, W = masks.shape
+    cap = int(cap or T * H * W)
+    pts = torch.empty(B, cap, dtype=torch.int32, device=masks.device)
+    counts = torch.empty(B, dtype=torch.int32, device=masks.device)
+    src = torch.empty(B, dtype=torch.int32, device=masks.device)
+    LIB.call("p2i_points_extract", ptr(_chk(masks, torch.float32, "masks")), B, T, H, W, ptr(pts), ptr(counts), ptr(src),
+             cap, stream())
+    return pts, counts, src
+
+
+def gate_points_fwd(masked: Tensor, pts: Tensor, counts: Tensor, w0, b0, w1, b1, save_l1: bool = False):
+    B, T, H, W = masked.shape
+    cap = pts.shape[1]
+    vals = torch.zeros(B, cap, dtype=torch.float32, device=masked.device)
+    l1 = torch.empty(B, cap, 16, dtype=torch.float32, device=masked.device) if save_l1 else None
+    LIB.call("p2i_gate_points_fwd", ptr(_chk(masked, torch.float32, "masked")), ptr(pts), ptr(counts), cap,
+             ptr(_chk(w0, torch.float32, "w0")), ptr(b0), ptr(_chk(w1, torch.float32, "w1")), ptr(b1), ptr(vals), ptr(l1),
+             B, T, H, W, stream())
+    return vals, l1
+
+
+def gate_points_bwd(masked, pts, counts, w0, b0, w1, b1, dvals):
+    B, T, H, W = masked.shape
+    cap = pts.shape[1]
+    dw0, db0, dw1, db1 = (torch.zeros_like(t, dtype=torch.float32) for t in (w0, b0, w1, b1))
+    LIB.call("p2i_gate_points_bwd", ptr(masked), ptr(pts), ptr(counts), cap, ptr(w0), ptr(b0), ptr(w1), ptr(b1),
+             ptr(_chk(dvals, torch.float32, "dvals")), ptr(dw0), ptr(db0), ptr(dw1), ptr(db1), B, T, H, W, stream())
+    return dw0, db0, dw1, db1
+
+
+def idw_knn_fwd(pts, vals, counts, src, shape: Tuple[int, int, int], tau: float, table=None):
+    """-> (out [B,T,H,W] f32, (nbr_idx, nbr_w)).  Pass `table` to reuse a neighbour table (no search)."""
+    T, H, W = shape
+    B, cap = pts.shape
+    Q = T * H * W
+    out = torch.empty(B, T, H, W, dtype=torch.float32, device=pts.device)
+    search = table is None
+    if search:
+        table = (torch.empty(B, Q, 4, dtype=torch.int32, device=pts.device),
+                 torch.empty(B, Q, 4, dtype=torch.float32, device=pts.device))
+    LIB.call("p2i_idw_knn_fwd", ptr(pts), ptr(vals), ptr(counts), ptr(src), cap, ptr(out), ptr(table[0]), ptr(table[1]),
+             B, T, H, W, float(tau), 1 if search else 0, stream())
+    return out, table
+
+
+def idw_knn_bwd(dout, table, counts, src, cap: int):
+    B, T, H, W = dout.shape
+    dvals = torch.zeros(B, cap, dtype=torch.float32, device=dout.device)
+    LIB.call("p2i_idw_knn_bwd", ptr(_chk(dout, torch.float32, "dout")), ptr(table[0]), ptr(table[1]), ptr(counts), ptr(src),
+             ptr(dvals), cap, B, T, H, W, stream())
+    return dvals
+
+
+# ------------------------------------------------------------------------------------------- convolutions
+def conv2d_cl(x: Tensor, w: Tensor, residual: Optional[Tensor] = None, relu: bool = False,
+              out: Optional[Tensor] = None, direct: bool = False) -> Tensor:
+    """x [B,H,W,Cin] bf16, w [k*k,Cout,Cin] bf16 -> [B,H,W,Cout] bf16 (tcgen05 implicit GEMM)."""
+    require_cuda(x, w)
+    B, H, W, Cin = x.shape
+    taps, Cout, Cin2 = w.shape
+    if Cin2 != Cin or taps not in (1, 9):
+        raise ValueError(f"conv2d_cl: weight {tuple(w.shape)} does not match input channels {Cin}")
+    k = 3 if taps == 9 else 1
+    if out is None:
+        out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x.device)
+    LIB.call("p2i_conv2d_direct_fwd" if direct else "p2i_conv2d_igemm_fwd", ptr(_chk(x, torch.bfloat16, "x")),
+             ptr(_chk(w, torch.bfloat16, "w")), ptr(residual), ptr(out), B, H, W, Cin, Cout, k, 1 if relu else 0, stream())
+    return out
+
+
+def doconv_compose(table_dev: Tensor, n_layers: int, max_channels: int) -> None:
+    LIB.call("p2i_doconv_compose_fwd", ptr(table_dev), n_layers, max_channels, stream())
+
+
+def doconv_compose_stem(W: Tensor, D: Tensor, D_diag: Tensor) -> Tensor:
+    out = torch.empty(64, 4, 9, dtype=torch.float32, device=W.device)
+    LIB.call("p2i_doconv_compose_stem_fwd", ptr(_chk(W, torch.float32, "W")), ptr(_chk(D, torch.float32, "D")),
+             ptr(_chk(D_diag, torch.float32, "D_diag")), ptr(out), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- generator glue
+def stem_fwd(x: Tensor, w: Tensor) -> Tensor:
+    B, C, H, W = x.shape
+    assert C == 16
+    y = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x.device)
+    LIB.call("p2i_stem_fwd", ptr(_chk(x, torch.float32, "x")), ptr(_chk(w, torch.float32, "w")), ptr(y), B, H, W, stream())
+    return y
+
+
+def pyramid_fwd(stem: Tensor):
+    B, H, W, C = stem.shape
+    assert C == 64
+    x4 = torch.empty(B, H // 4, W // 4, 256, dtype=torch.bfloat16, device=stem.device)
+    x8 = torch.empty(B, H // 8, W // 8, 512, dtype=torch.bfloat16, device=stem.device)
+    LIB.call("p2i_pyramid_fwd", ptr(_chk(stem, torch.bfloat16, "stem")), ptr(x4), ptr(x8), B, H, W, stream())
+    return x4, x8
+
+
+def upmod_fwd(z: Tensor, pos: Tensor, bias: Tensor, skip: Optional[Tensor] = None) -> Tensor:
+    B, h, w, C = z.shape
+    out = torch.empty(B, 2 * h, 2 * w, C, dtype=torch.bfloat16, device=z.device)
+    LIB.call("p2i_upmod_fwd", ptr(_chk(z, torch.bfloat16, "z")), ptr(_chk(pos, torch.float32, "pos")),
+             ptr(_chk(bias, torch.float32, "bias")), ptr(skip), ptr(out), B, h, w, C, stream())
+    return out
+
+
+def head_fwd(x: Tensor, w: Tensor, want_pre: bool = False):
+    B, H, W, C = x.shape
+    assert C == 64
+    out = torch.empty(B, 16, H, W, dtype=torch.float32, device=x.device)
+    pre = torch.empty_like(out) if want_pre else None
+    LIB.call("p2i_head_fwd", ptr(_chk(x, torch.bfloat16, "x")), ptr(_chk(w, torch.float32, "w")), ptr(out), ptr(pre), B, H, W,
+             stream())
+    return (out, pre) if want_pre else out
+
+
+def to_cl(x: Tensor) -> Tensor:
+    """NCHW f32 -> NHWC bf16."""
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=x.device)
+    LIB.call("p2i_nchw_f32_to_nhwc_bf16", ptr(_chk(x, torch.float32, "x")), ptr(y), B, C, H, W, stream())
+    return y
+
+
+def from_cl(x: Tensor) -> Tensor:
+    """NHWC bf16 -> NCHW f32."""
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    LIB.call("p2i_nhwc_bf16_to_nchw_f32", ptr(_chk(x, torch.bfloat16, "x")), ptr(y), B, C, H, W, stream())
+    return y
