@@ -83,23 +83,50 @@ typedef struct P2iDoLayer {
 
 /* One launch for a whole table of groups=1, 3x3 DO-Conv layers (device-resident table). */
 int p2i_doconv_compose_fwd(const P2iDoLayer* table_dev, int n_layers, int max_channels, void* stream);
+typedef struct P2iDoGrad {
+    const float* W;      /* [C, C, 9] */
+    const float* D;      /* [C, 9, 9] */
+    const float* D_diag; /* [C, 9, 9] */
+    const float* dDoW;   /* f32 [9][C][C]: output of p2i_conv2d_wgrad */
+    float* dW;           /* [C, C, 9] (overwritten) */
+    float* dD;           /* [C, 9, 9] (overwritten) */
+    int channels;
+    int _pad;
+} P2iDoGrad;
+
+/* Backward of the composition for a table of layers (torch.einsum backward at deconv_pytorch.py:124):
+ * dW[o,i,s] = sum_m dDoW[m,o,i] (D+D_diag)[i,m,s] ;  dD[i,m,s] = sum_o dDoW[m,o,i] W[o,i,s]. */
+int p2i_doconv_compose_bwd(const P2iDoGrad* table_dev, int n_layers, int max_channels, void* stream);
+
 /* Grouped stem variant (Convsin: 16->64, k3, groups 4) keeping the reference's raw-reshape row
  * pairing (deconv_pytorch.py:119-124).  out f32 [64,4,9]. */
 int p2i_doconv_compose_stem_fwd(const float* W, const float* D, const float* D_diag, float* out, void* stream);
+/* dDoW f32 [64,4,9] -> dW [64,4,9], dD [16,9,9]. */
+int p2i_doconv_compose_stem_bwd(const float* W, const float* D, const float* D_diag, const float* dDoW, float* dW,
+                                float* dD, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolutions as tcgen05 implicit GEMM  (F.conv2d at deconv_pytorch.py:108; layer.py:129-135)
  * ------------------------------------------------------------------------------------------- */
 
-/* y = act(conv(x, w) [+ residual]);  x [B,H,W,Cin] bf16, w [k*k][Cout][Cin] bf16, y [B,H,W,Cout] bf16.
- * ksize in {1,3}, stride 1, zero padding k/2.  Cin % 64 == 0, Cout % 64 == 0.
- * flags: bit0 = ReLU after the residual add.  residual may be NULL. */
+/* y = mask( act( conv(x, w) + bias + residual ) );
+ * x [B,H,W,Cin] bf16, w [k*k][Cout][Cin] bf16, y [B,H,W,Cout] bf16.  ksize in {1,3}, stride 1, zero padding k/2.
+ * Cin % 64 == 0, Cout % 64 == 0.  residual / mask (bf16 [B,H,W,Cout]) and bias (f32 [Cout]) may be NULL.
+ * mask: the output is zeroed where mask <= 0 -- the ReLU backward fused into a dgrad launch.
+ * The data gradient of the same convolution is this entry point called with dY as x and the
+ * transposed, tap-flipped weights ([k*k][Cin][Cout], produced by p2i_doconv_compose_fwd's out_t). */
 #define P2I_CONV_RELU 1
-int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W, int Cin,
-                         int Cout, int ksize, int flags, void* stream);
+#define P2I_CONV_LEAKY 2 /* LeakyReLU(0.2) */
+int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, const void* mask, const float* bias,
+                         void* y, int B, int H, int W, int Cin, int Cout, int ksize, int flags, void* stream);
 /* CUDA-core direct convolution with identical semantics (test/triage only; never on the product path). */
-int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W, int Cin,
-                          int Cout, int ksize, int flags, void* stream);
+int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, const void* mask, const float* bias,
+                          void* y, int B, int H, int W, int Cin, int Cout, int ksize, int flags, void* stream);
+
+/* Weight gradient: dW[tap][co][ci] += sum_pix dy[pix][co] * x[pix+tap][ci]  (fp32 [k*k][Cout][Cin], atomically
+ * accumulated: the caller zero-fills).  x [B,H,W,Cin], dy [B,H,W,Cout] bf16.  Cin in {64} or % 128 == 0. */
+int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B, int H, int W, int Cin, int Cout, int ksize,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Generator glue  (p2igan_bench/models/p2igan.py:72-112)
@@ -122,6 +149,41 @@ int p2i_upmod_fwd(const void* z, const float* pos, const float* bias, const void
 /* ConvsOut (1x1, groups 4, 64->16) + tanh  (p2igan.py:109-111).
  * x [B,H,W,64] bf16, w f32 [16,16] -> out f32 [B,16,H,W]; pre (optional) receives the pre-tanh z. */
 int p2i_head_fwd(const void* x, const float* w, float* out, float* pre, int B, int H, int W, void* stream);
+
+/* ---- backward of the glue ---- */
+/* dout, out f32 [B,16,H,W] (out = tanh output), x [B,H,W,64] bf16 -> dx [B,H,W,64] bf16; dw f32 [16,16] accumulated. */
+int p2i_head_bwd(const float* dout, const float* out, const void* x, const float* w, void* dx, float* dw, int B, int H,
+                 int W, void* stream);
+/* UPPos tail backward. dout [B,2h,2w,C] bf16 (gradient of the pre-skip ReLU output; the skip branch receives the
+ * same tensor).  g_scratch [B,2h,2w,C] bf16 workspace.  dz [B,h,w,C] bf16 (overwritten); dbias f32 [C] and
+ * dpos f32 [2h,2w] are accumulated (caller zero-fills). */
+int p2i_upmod_bwd(const void* z, const float* pos, const float* bias, const void* dout, void* g_scratch, void* dz,
+                  float* dbias, float* dpos, int B, int h, int w, int C, void* stream);
+/* d(x4) [B,H/4,W/4,256], d(x8) [B,H/8,W/8,512] -> d(stem) [B,H,W,64] bf16 (overwritten), routed to the arg-max
+ * pixels of the saved stem output (max_pool2d backward + repeat_interleave backward, layer.py:210-213). */
+int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx8, void* dstem, int B, int H, int W, void* stream);
+/* dy [B,H,W,64] bf16, x f32 [B,16,H,W], w f32 [64,4,9] -> dx f32 [B,16,H,W] (overwritten), dw f32 [64,4,9] accumulated. */
+int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses  (p2igan_bench/modules/losses.py:38-85, 192-253)
+ * ------------------------------------------------------------------------------------------- */
+
+/* ReconstructionLoss forward.  pred/target f32 [B,T,HW].  sums[0] += sum w(y)|p-y| (weighted L1 numerator),
+ * sums[1] += sum over the B*(T-1) temporal-difference rows of KL(q||p) with p,q = softmax(diff/temperature);
+ * lse f32 [B*(T-1),2] receives the per-row log-sum-exp (kept for the backward).  Caller zero-fills sums.
+ * loss = sums[0]/(B*T*HW) + k1_alpha * sums[1]/B. */
+int p2i_rec_loss_fwd(const float* pred, const float* target, int B, int T, int HW, float temperature, float* sums,
+                     float* lse, void* stream);
+/* d loss / d pred (closed form), scaled by *gscale (device scalar, NULL = 1). dpred f32 [B,T,HW] overwritten. */
+int p2i_rec_loss_bwd(const float* pred, const float* target, const float* lse, const float* gscale, float k1_alpha,
+                     float temperature, float* dpred, int B, int T, int HW, void* stream);
+/* AdversarialLoss: *out += mean(term(x)).  mode 0: relu(1-x) (hinge, D real) | 1: relu(1+x) (hinge, D fake) |
+ * 2: -x (hinge, G) | 3: BCE(x, label) on raw outputs (nsgan, losses.py:203) | 4: (x-label)^2 (lsgan). */
+int p2i_gan_loss_fwd(const float* logits, long long n, int mode, float label, float* out, void* stream);
+/* dlogits = (*gscale) * scale * d mean(term) / dx. */
+int p2i_gan_loss_bwd(const float* logits, long long n, int mode, float label, const float* gscale, float scale,
+                     float* dlogits, void* stream);
 
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);

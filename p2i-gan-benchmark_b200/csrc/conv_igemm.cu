@@ -26,8 +26,10 @@ struct ConvParams {
     int KH, KW;
     int Ht, Wt;
     int tiles_x, tiles_y, m_tiles, total_tiles;
-    int relu;
-    const __nv_bfloat16* residual;
+    int relu;                          // 1 = ReLU, 2 = LeakyReLU(0.2)
+    const __nv_bfloat16* residual;     // added before the activation
+    const __nv_bfloat16* mask;         // output zeroed where mask <= 0 (ReLU backward fused into dgrad)
+    const float* bias;                 // per output channel, fp32
     __nv_bfloat16* y;
 };
 
@@ -172,6 +174,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     float f[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * NT + c);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bv = __ldg(bp + i);
+                            f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
+                        }
+                    }
                     if (p.residual != nullptr) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
                         uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
@@ -183,9 +193,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             f[2 * i + 1] += t.y;
                         }
                     }
-                    if (p.relu) {
+                    if (p.relu == 1) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                    } else if (p.relu == 2) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+                    }
+                    if (p.mask != nullptr) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off + c);
+                        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                        const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float2 t = unpack_bf16x2(mm[i]);
+                            if (!(t.x > 0.f)) f[2 * i] = 0.f;
+                            if (!(t.y > 0.f)) f[2 * i + 1] = 0.f;
+                        }
                     }
                     uint4 o0, o1;
                     o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
@@ -228,7 +252,8 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 // CUDA-core direct convolution: same contract, used by tests to triage the tensor-core kernel.
 // --------------------------------------------------------------------------------------------
 __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                                   const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, int B, int H,
+                                   const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ mask,
+                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H,
                                    int W, int Cin, int Cout, int K, int relu) {
     const long long total = static_cast<long long>(B) * H * W * Cout;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -250,8 +275,11 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
                 for (int ci = 0; ci < Cin; ++ci) acc += __bfloat162float(xp[ci]) * __bfloat162float(wp[ci]);
             }
         }
+        if (bias) acc += bias[co];
         if (res) acc += __bfloat162float(res[i]);
-        if (relu) acc = fmaxf(acc, 0.f);
+        if (relu == 1) acc = fmaxf(acc, 0.f);
+        else if (relu == 2) acc = acc > 0.f ? acc : 0.2f * acc;
+        if (mask && !(__bfloat162float(mask[i]) > 0.f)) acc = 0.f;
         y[i] = __float2bfloat16(acc);
     }
 }
@@ -260,8 +288,9 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
 
 using namespace p2i;
 
-extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W,
-                                    int Cin, int Cout, int ksize, int flags, void* stream) {
+extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, const void* mask,
+                                    const float* bias, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                                    int flags, void* stream) {
     P2I_CHECK_ARG(x && w && y, "conv2d_igemm: null pointer");
     P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_igemm: ksize %d unsupported (1 or 3)", ksize);
     P2I_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape B=%d H=%d W=%d", B, H, W);
@@ -275,8 +304,10 @@ extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* re
     p.tiles_x = cdiv(W, p.Wt);
     p.tiles_y = cdiv(H, p.Ht);
     p.m_tiles = B * p.tiles_x * p.tiles_y;
-    p.relu = (flags & P2I_CONV_RELU) ? 1 : 0;
+    p.relu = (flags & P2I_CONV_RELU) ? 1 : ((flags & P2I_CONV_LEAKY) ? 2 : 0);
     p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.mask = static_cast<const __nv_bfloat16*>(mask);
+    p.bias = bias;
     p.y = static_cast<__nv_bfloat16*>(y);
     const int NT = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     p.total_tiles = p.m_tiles * (Cout / NT);
@@ -302,16 +333,18 @@ extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* re
     return launch_conv<64>(tmA, tmB, p, st);
 }
 
-extern "C" int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, void* y, int B, int H, int W,
-                                     int Cin, int Cout, int ksize, int flags, void* stream) {
+extern "C" int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, const void* mask,
+                                     const float* bias, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                                     int flags, void* stream) {
     P2I_CHECK_ARG(x && w && y, "conv2d_direct: null pointer");
     P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_direct: ksize %d unsupported", ksize);
     const long long total = static_cast<long long>(B) * H * W * Cout;
     int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     conv_direct_kernel<<<grid, 256, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
-        static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), B, H, W, Cin, Cout, ksize,
-        (flags & P2I_CONV_RELU) ? 1 : 0);
+        static_cast<const __nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(mask), bias,
+        static_cast<__nv_bfloat16*>(y), B, H, W, Cin, Cout, ksize,
+        (flags & P2I_CONV_RELU) ? 1 : ((flags & P2I_CONV_LEAKY) ? 2 : 0));
     P2I_CHECK_LAUNCH("conv_direct_kernel");
     return P2I_OK;
 }

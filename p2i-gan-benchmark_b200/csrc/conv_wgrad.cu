@@ -1,0 +1,208 @@
+// Weight gradient of the stride-1 k x k convolutions as a tcgen05 GEMM whose reduction (K) axis is the
+// PIXEL axis:   dW[tap][co][ci] = sum_pix dY[pix][co] * X[pix + tap][ci]
+// (backward of F.conv2d at p2igan_bench/modules/deconv_pytorch.py:108 w.r.t. its weight, and of the
+//  UPPos 1x1 projection, layer.py:390).
+//
+// Both operands are NHWC bf16 tiles fetched by TMA exactly as in the forward kernel ([pixels][64 channels],
+// 128 B per pixel, 128B swizzle).  With pixels as K they are "MN-major" UMMA operands: the 64 channels of
+// a pixel are the contiguous M/N atom, 8 pixels form a 1024-B K group (SBO), further 64-channel atoms are
+// LBO bytes apart.
+//   A (M side) = X halo tile: (Ht+k-1) x Wt pixels.  The vertical taps are row-shifted views (ky*Wt pixels,
+//                a multiple of 1024 B) of the same box, as in the forward kernel.
+//   B (N side) = dY tile: Ht x Wt pixels, NT output channels.
+//   D[ci][co]  = one fp32 TMEM accumulator per vertical tap, accumulated over all pixel tiles of the CTA's
+//                K split, then reduced into dW with coalesced fp32 atomics (lanes = consecutive ci).
+// Work item = (kx, ci tile, co tile, K split).  C = 64 layers stack two vertical taps into one M = 128
+// instruction (second atom = the view one tile row further down: LBO = Wt*128 B).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace p2i {
+
+struct WgradParams {
+    int B, H, W, Cin, Cout;
+    int KH, KW;
+    int Ht, Wt, tiles_x, tiles_y, pix_tiles;
+    int ci_tiles, co_tiles, ksplit;
+    int stacked;     // 1: Cin tile = 64 channels, two vertical taps per MMA
+    int nt;          // co tile width (64 or 128)
+    float* dW;       // [KH*KW][Cout][Cin] fp32, accumulated with atomics (caller zero-fills)
+};
+
+constexpr int WG_STAGES = 3;
+constexpr int WG_X_ATOM = 20480;   // (8+2)*16*128 B, also >= (16+2)*8*128
+constexpr int WG_Y_ATOM = 16384;
+constexpr int WG_STAGE_BYTES = 2 * WG_X_ATOM + 2 * WG_Y_ATOM;   // 73728
+constexpr int WG_SMEM = 1024 + WG_STAGES * WG_STAGE_BYTES + 64;
+
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* done = empty + WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = p.stacked ? 2 : p.KH;             // accumulators per CTA
+    const uint32_t tmem_cols = (ngroups * p.nt <= 128) ? 128 : ((ngroups * p.nt <= 256) ? 256 : 512);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); }
+    if (warp == 2) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item decode
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    const int cot = item % p.co_tiles; item /= p.co_tiles;
+    const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+    const int kx = item;
+    const int ci_atoms = p.stacked ? 1 : 2;
+    const int co_atoms = p.nt >> 6;
+    const int ci0 = cit * (p.stacked ? 64 : 128), co0 = cot * p.nt;
+    const int t_begin = static_cast<int>(static_cast<long long>(p.pix_tiles) * ks / p.ksplit);
+    const int t_end = static_cast<int>(static_cast<long long>(p.pix_tiles) * (ks + 1) / p.ksplit);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const uint32_t x_bytes = static_cast<uint32_t>((p.Ht + p.KH - 1) * p.Wt * 128);
+    const uint32_t stage_tx = ci_atoms * x_bytes + co_atoms * WG_Y_ATOM;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t s = 0, ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * p.Ht, x0 = (r % p.tiles_x) * p.Wt;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], stage_tx);
+                uint8_t* st = smem + s * WG_STAGE_BYTES;
+                for (int a = 0; a < ci_atoms; ++a)
+                    tma_load_4d(st + a * WG_X_ATOM, &tmX, &full[s], ci0 + a * 64, x0 + kx - (p.KW >> 1), y0 - (p.KH >> 1), b);
+                for (int a = 0; a < co_atoms; ++a)
+                    tma_load_4d(st + 2 * WG_X_ATOM + a * WG_Y_ATOM, &tmY, &full[s], co0 + a * 64, x0, y0, b);
+                if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.nt, 1, 1);
+            const uint32_t row_shift = static_cast<uint32_t>(p.Wt * 128);
+            uint32_t s = 0, ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t xb = smem_u32(smem + s * WG_STAGE_BYTES);
+                const uint32_t yb = xb + 2 * WG_X_ATOM;
+                const uint32_t acc = (t > t_begin) ? 1u : 0u;
+                for (int g = 0; g < ngroups; ++g) {
+                    // stacked: group g covers vertical taps 2g, 2g+1 (atoms one tile-row apart)
+                    const uint32_t a0 = xb + (p.stacked ? 2 * g : g) * row_shift;
+                    const uint32_t a_lbo = p.stacked ? row_shift : static_cast<uint32_t>(WG_X_ATOM);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        umma_bf16(tmem_base + g * p.nt, make_sw128_desc(a0 + k * 2048, a_lbo, 1024),
+                                  make_sw128_desc(yb + k * 2048, WG_Y_ATOM, 1024), idesc, acc | (k > 0 ? 1u : 0u));
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(done);
+        }
+    } else if (warp >= 4 && t_end > t_begin) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        for (int g = 0; g < ngroups; ++g) {
+            int ky, ci;
+            bool ok = true;
+            if (p.stacked) {
+                ky = 2 * g + (row >> 6);
+                ci = ci0 + (row & 63);
+                ok = ky < p.KH;
+            } else {
+                ky = g;
+                ci = ci0 + row;
+            }
+            const int tap = ky * p.KW + kx;
+            float* dst = p.dW + (static_cast<size_t>(tap) * p.Cout + co0) * p.Cin + ci;
+            const uint32_t t_addr = tmem_base + g * p.nt + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < p.nt; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + c, v);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<size_t>(c + i) * p.Cin, __uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B, int H, int W, int Cin, int Cout,
+                                int ksize, void* stream) {
+    P2I_CHECK_ARG(x && dy && dW, "conv2d_wgrad: null pointer");
+    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize %d unsupported", ksize);
+    P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "conv2d_wgrad: channels must be multiples of 64");
+    P2I_CHECK_ARG(Cin == 64 || Cin % 128 == 0, "conv2d_wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
+    WgradParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = ksize; p.KW = ksize;
+    p.Wt = (W >= 16) ? 16 : 8;
+    p.Ht = 128 / p.Wt;
+    p.tiles_x = cdiv(W, p.Wt);
+    p.tiles_y = cdiv(H, p.Ht);
+    p.pix_tiles = B * p.tiles_x * p.tiles_y;
+    p.stacked = (Cin == 64) ? 1 : 0;
+    p.nt = (Cout % 128 == 0) ? 128 : 64;
+    p.ci_tiles = p.stacked ? 1 : Cin / 128;
+    p.co_tiles = Cout / p.nt;
+    const int items = p.KW * p.ci_tiles * p.co_tiles;
+    int ks = cdiv(sm_count(), items);
+    if (ks > p.pix_tiles) ks = p.pix_tiles;
+    if (ks < 1) ks = 1;
+    p.ksplit = ks;
+    p.dW = dW;
+
+    CUtensorMap tmX, tmY;
+    {
+        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
+        const uint64_t strides[4] = {0, uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
+        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht + ksize - 1), 1};
+        int rc = encode_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr, true);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {uint64_t(Cout), uint64_t(W), uint64_t(H), uint64_t(B)};
+        const uint64_t strides[4] = {0, uint64_t(Cout) * 2, uint64_t(W) * Cout * 2, uint64_t(H) * W * Cout * 2};
+        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht), 1};
+        int rc = encode_tmap_bf16(&tmY, dy, 4, dims, strides, box, nullptr, true);
+        if (rc) return rc;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_wgrad smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_wgrad_kernel<<<items * ks, 256, WG_SMEM, as_stream(stream)>>>(tmX, tmY, p);
+    P2I_CHECK_LAUNCH("conv_wgrad_kernel");
+    return P2I_OK;
+}

@@ -78,3 +78,118 @@ extern "C" int p2i_doconv_compose_stem_fwd(const float* W, const float* D, const
     P2I_CHECK_LAUNCH("doconv_compose_stem_kernel");
     return P2I_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the composition.  dDoW is the fp32 wgrad output [m][o][i] (same layout as `out`).
+//   dW[o,i,s] = sum_m dDoW[m,o,i] * (D + D_diag)[i,m,s]
+//   dD[i,m,s] = sum_o dDoW[m,o,i] * W[o,i,s]
+// ------------------------------------------------------------------------------------------------
+namespace p2i {
+
+__global__ void __launch_bounds__(256) doconv_bwd_w_kernel(const P2iDoGrad* __restrict__ table) {
+    const P2iDoGrad L = table[blockIdx.z];
+    const int C = L.channels;
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+    if (i0 >= C || o0 >= C) return;
+    __shared__ float sD[32][82];
+    for (int e = threadIdx.x; e < 32 * 81; e += 256) {
+        const int ii = e / 81, r = e - ii * 81;
+        const size_t g = static_cast<size_t>(i0 + ii) * 81 + r;
+        sD[ii][r] = L.D[g] + L.D_diag[g];
+    }
+    __syncthreads();
+    const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
+    const int i = i0 + ii;
+    for (int o = o0 + oo; o < o0 + 64; o += 8) {
+        float g[9];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) g[m] = L.dDoW[(static_cast<size_t>(m) * C + o) * C + i];
+        float* wp = L.dW + (static_cast<size_t>(o) * C + i) * 9;
+#pragma unroll
+        for (int s = 0; s < 9; ++s) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < 9; ++m) acc = fmaf(g[m], sD[ii][m * 9 + s], acc);
+            wp[s] = acc;
+        }
+    }
+}
+
+// block = 32 input channels x 8 output-channel lanes; each thread owns the full 9x9 of its input channel
+// over its share of output channels, then the 8 lanes are reduced through shared memory.
+__global__ void __launch_bounds__(256) doconv_bwd_d_kernel(const P2iDoGrad* __restrict__ table) {
+    const P2iDoGrad L = table[blockIdx.z];
+    const int C = L.channels;
+    const int i0 = blockIdx.x * 32;
+    if (i0 >= C) return;
+    __shared__ float red[32][82];
+    for (int e = threadIdx.x; e < 32 * 82; e += 256) (&red[0][0])[e] = 0.f;
+    __syncthreads();
+    const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
+    const int i = i0 + ii;
+    float acc[81];
+#pragma unroll
+    for (int k = 0; k < 81; ++k) acc[k] = 0.f;
+    for (int o = oo; o < C; o += 8) {
+        float g[9], w[9];
+        const float* wp = L.W + (static_cast<size_t>(o) * C + i) * 9;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+            g[m] = L.dDoW[(static_cast<size_t>(m) * C + o) * C + i];
+            w[m] = wp[m];
+        }
+#pragma unroll
+        for (int m = 0; m < 9; ++m)
+#pragma unroll
+            for (int s = 0; s < 9; ++s) acc[m * 9 + s] = fmaf(g[m], w[s], acc[m * 9 + s]);
+    }
+#pragma unroll
+    for (int k = 0; k < 81; ++k) atomicAdd(&red[ii][k], acc[k]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 81; e += 256) {
+        const int a = e / 81, r = e - a * 81;
+        L.dD[static_cast<size_t>(i0 + a) * 81 + r] = red[a][r];
+    }
+}
+
+// stem: dDoW f32 [64][4][9] -> dW [64,4,9], dD [16,9,9] with the reference's raw-reshape row pairing
+__global__ void doconv_bwd_stem_kernel(const float* __restrict__ W, const float* __restrict__ D, const float* __restrict__ Dd,
+                                       const float* __restrict__ g, float* __restrict__ dW, float* __restrict__ dD) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 64 * 4 * 9) {            // dW[oc][icl][s] = sum_m g[oc][icl][m] * Dsum[i][m][s]
+        const int s = idx % 9, icl = (idx / 9) % 4, oc = idx / 36;
+        const int i = (oc % 4) * 4 + icl;
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) acc = fmaf(g[(oc * 4 + icl) * 9 + m], D[(i * 9 + m) * 9 + s] + Dd[(i * 9 + m) * 9 + s], acc);
+        dW[idx] = acc;
+    }
+    if (idx < 16 * 81) {               // dD[i][m][s] = sum over (oc, icl) with (oc%4)*4+icl == i
+        const int s = idx % 9, m = (idx / 9) % 9, i = idx / 81;
+        const int icl = i % 4, r = i / 4;
+        float acc = 0.f;
+        for (int oc = r; oc < 64; oc += 4) acc = fmaf(g[(oc * 4 + icl) * 9 + m], W[(oc * 4 + icl) * 9 + s], acc);
+        dD[idx] = acc;
+    }
+}
+
+}  // namespace p2i
+
+extern "C" int p2i_doconv_compose_bwd(const P2iDoGrad* table_dev, int n_layers, int max_channels, void* stream) {
+    P2I_CHECK_ARG(table_dev && n_layers > 0 && max_channels % 64 == 0, "doconv_compose_bwd: bad table");
+    dim3 gw(max_channels / 32, max_channels / 64, n_layers);
+    p2i::doconv_bwd_w_kernel<<<gw, 256, 0, p2i::as_stream(stream)>>>(table_dev);
+    P2I_CHECK_LAUNCH("doconv_bwd_w_kernel");
+    dim3 gd(max_channels / 32, 1, n_layers);
+    p2i::doconv_bwd_d_kernel<<<gd, 256, 0, p2i::as_stream(stream)>>>(table_dev);
+    P2I_CHECK_LAUNCH("doconv_bwd_d_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_doconv_compose_stem_bwd(const float* W, const float* D, const float* D_diag, const float* dDoW,
+                                           float* dW, float* dD, void* stream) {
+    P2I_CHECK_ARG(W && D && D_diag && dDoW && dW && dD, "doconv_compose_stem_bwd: null pointer");
+    p2i::doconv_bwd_stem_kernel<<<p2i::cdiv(64 * 4 * 9, 256), 256, 0, p2i::as_stream(stream)>>>(W, D, D_diag, dDoW, dW, dD);
+    P2I_CHECK_LAUNCH("doconv_bwd_stem_kernel");
+    return P2I_OK;
+}

@@ -1,0 +1,435 @@
+// Backward of the HBM-bound generator glue (see gen_glue.cu for the forward and the reference citations).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace p2i {
+
+// ------------------------------------------------------------------------------------------------
+// ConvsOut + tanh backward (p2igan.py:109-111):  dz = dout * (1 - out^2);
+//   dx[16g+i] = sum_{o in group g} dz[o] * w[o][i] ;  dw[o][i] += sum_pix dz[o] * x[16g+i]
+// 4 threads per pixel (one per group) so that the 128-B pixel rows are read/written coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                       const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, long long npix,
+                                                       int HW) {
+    __shared__ float sw[256];
+    __shared__ float sdw[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+    __syncthreads();
+    const int g = threadIdx.x & 3;
+    float acc[4][16];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[o][i] = 0.f;
+    for (long long p = static_cast<long long>(blockIdx.x) * 64 + (threadIdx.x >> 2); p < npix;
+         p += static_cast<long long>(gridDim.x) * 64) {
+        const int b = static_cast<int>(p / HW), pix = static_cast<int>(p - static_cast<long long>(b) * HW);
+        float dz[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const size_t oi = (static_cast<size_t>(b) * 16 + g * 4 + o) * HW + pix;
+            const float t = out[oi];
+            dz[o] = dout[oi] * (1.f - t * t);
+        }
+        const uint4* xp = reinterpret_cast<const uint4*>(x + p * 64 + g * 16);
+        const uint4 u0 = __ldg(xp), u1 = __ldg(xp + 1);
+        const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float in[16], d[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = unpack_bf16x2(uu[i]);
+            in[2 * i] = f.x;
+            in[2 * i + 1] = f.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                s = fmaf(dz[o], sw[(g * 4 + o) * 16 + i], s);
+                acc[o][i] = fmaf(dz[o], in[i], acc[o][i]);
+            }
+            d[i] = s;
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(d[0], d[1]);   o0.y = pack_bf16x2(d[2], d[3]);
+        o0.z = pack_bf16x2(d[4], d[5]);   o0.w = pack_bf16x2(d[6], d[7]);
+        o1.x = pack_bf16x2(d[8], d[9]);   o1.y = pack_bf16x2(d[10], d[11]);
+        o1.z = pack_bf16x2(d[12], d[13]); o1.w = pack_bf16x2(d[14], d[15]);
+        uint4* dp = reinterpret_cast<uint4*>(dx + p * 64 + g * 16);
+        dp[0] = o0;
+        dp[1] = o1;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(&sdw[(g * 4 + o) * 16 + i], acc[o][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// UPPos tail backward, pass 1 (high resolution): recompute pre = s*up(z)+bias,
+//   dpre = (pre > 0) ? dout : 0 ;  g = s * dpre (bf16, input of the transposed upsample)
+//   dbias[c] += sum dpre ;  dpos[Y,X] = s*(1 - s/2) * sum_{b,c} dpre * up(z)
+// one thread per (pixel, 8 channels); a pixel's C/8 threads are consecutive.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ pos,
+                                                           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ dout,
+                                                           __nv_bfloat16* __restrict__ gout, float* __restrict__ dbias,
+                                                           float* __restrict__ dpos, int B, int h, int w, int C) {
+    extern __shared__ float s_db[];   // [C]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
+    __syncthreads();
+    const int cg = C >> 3;
+    const long long total = static_cast<long long>(B) * 4 * h * w * cg;
+    const int H2 = 2 * h, W2 = 2 * w;
+    const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
+    const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % cg);
+        const long long pix = idx / cg;
+        const int X = static_cast<int>(pix % W2), Y = static_cast<int>((pix / W2) % H2);
+        const int b = static_cast<int>(pix / (static_cast<long long>(W2) * H2));
+        const float fy = sy * Y, fx = sx * X;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - y0, lx = fx - x0;
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        const float s = 2.f / (1.f + __expf(-pos[static_cast<size_t>(Y) * W2 + X]));
+        const uint4* zb = reinterpret_cast<const uint4*>(z + static_cast<size_t>(b) * h * w * C) + c8;
+        const uint4 a = __ldg(zb + (static_cast<size_t>(y0) * w + x0) * cg), bq = __ldg(zb + (static_cast<size_t>(y0) * w + x1) * cg);
+        const uint4 c = __ldg(zb + (static_cast<size_t>(y1) * w + x0) * cg), d = __ldg(zb + (static_cast<size_t>(y1) * w + x1) * cg);
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+        const uint32_t cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+        const size_t o = static_cast<size_t>(pix) * cg + c8;
+        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(dout) + o);
+        const uint32_t gv[4] = {gq.x, gq.y, gq.z, gq.w};
+        const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2);
+        const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2 + 1);
+        const float bb[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
+        uint32_t ov[4];
+        float ds = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = unpack_bf16x2(av[i]), fb = unpack_bf16x2(bv[i]), fc = unpack_bf16x2(cv[i]), fd = unpack_bf16x2(dv[i]);
+            const float2 gg = unpack_bf16x2(gv[i]);
+            const float u0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+            const float u1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+            const float d0 = (fmaf(s, u0, bb[2 * i]) > 0.f) ? gg.x : 0.f;
+            const float d1 = (fmaf(s, u1, bb[2 * i + 1]) > 0.f) ? gg.y : 0.f;
+            ds += d0 * u0 + d1 * u1;
+            if (d0 != 0.f) atomicAdd(&s_db[c8 * 8 + 2 * i], d0);
+            if (d1 != 0.f) atomicAdd(&s_db[c8 * 8 + 2 * i + 1], d1);
+            ov[i] = pack_bf16x2(s * d0, s * d1);
+        }
+        reinterpret_cast<uint4*>(gout)[o] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        // reduce ds over the pixel's cg consecutive threads (cg is a power of two >= 8; groups never straddle a warp
+        // when cg <= 32, otherwise every warp holds a single pixel)
+        const int span = cg < 32 ? cg : 32;
+        for (int off = span >> 1; off > 0; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
+        if ((threadIdx.x & (span - 1)) == 0 && ds != 0.f)
+            atomicAdd(&dpos[static_cast<size_t>(Y) * W2 + X], ds * s * (1.f - 0.5f * s));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+        if (s_db[i] != 0.f) atomicAdd(&dbias[i], s_db[i]);
+}
+
+// pass 2 (low resolution): dz = transpose(bilinear x2, align_corners) applied to g.  Gather form: every
+// low-res pixel visits the (at most 5x5) high-res pixels whose interpolation footprint contains it.
+__global__ void __launch_bounds__(256) upmod_bwd_lo_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dz,
+                                                           int B, int h, int w, int C) {
+    const int cg = C >> 3;
+    const long long total = static_cast<long long>(B) * h * w * cg;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cg);
+    const long long pix = idx / cg;
+    const int x = static_cast<int>(pix % w), y = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const int H2 = 2 * h, W2 = 2 * w;
+    const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
+    const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
+    // candidate high-res rows: those with floor(sy*Y) in {y-1, y}
+    int Ya = (sy > 0.f) ? static_cast<int>(floorf((y - 1) / sy)) - 1 : 0, Yb = (sy > 0.f) ? static_cast<int>(ceilf((y + 1) / sy)) + 1 : H2 - 1;
+    int Xa = (sx > 0.f) ? static_cast<int>(floorf((x - 1) / sx)) - 1 : 0, Xb = (sx > 0.f) ? static_cast<int>(ceilf((x + 1) / sx)) + 1 : W2 - 1;
+    Ya = Ya < 0 ? 0 : Ya; Xa = Xa < 0 ? 0 : Xa;
+    Yb = Yb > H2 - 1 ? H2 - 1 : Yb; Xb = Xb > W2 - 1 ? W2 - 1 : Xb;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint4* gb = reinterpret_cast<const uint4*>(g + static_cast<size_t>(b) * H2 * W2 * C) + c8;
+    for (int Y = Ya; Y <= Yb; ++Y) {
+        const float fy = sy * Y;
+        const int y0 = static_cast<int>(fy);
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+        const float ly = fy - y0;
+        const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+        if (wy == 0.f) continue;
+        for (int X = Xa; X <= Xb; ++X) {
+            const float fx = sx * X;
+            const int x0 = static_cast<int>(fx);
+            const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+            const float lx = fx - x0;
+            const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+            if (wx == 0.f) continue;
+            const float wt = wy * wx;
+            const uint4 q = __ldg(gb + (static_cast<size_t>(Y) * W2 + X) * cg);
+            const uint32_t qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(qv[i]);
+                acc[2 * i] = fmaf(wt, f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(wt, f.y, acc[2 * i + 1]);
+            }
+        }
+    }
+    reinterpret_cast<uint4*>(dz)[static_cast<size_t>(pix) * cg + c8] =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid backward: route d(x4), d(x8) to the arg-max pixel of each 4x4 / 8x8 block of the stem output.
+// Ties follow nested 2x2 max-pools (first element in window order wins at every level, as ATen's
+// max_pool2d backward does).  One warp per 8x8 block, lane = channel pair; writes all 64 pixels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void argmax2x2(const float (&v)[4], const int (&id)[4], float& mv, int& mi) {
+    mv = v[0]; mi = id[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (v[k] > mv) { mv = v[k]; mi = id[k]; }
+}
+
+__global__ void __launch_bounds__(256) pyramid_bwd_kernel(const __nv_bfloat16* __restrict__ stem, const __nv_bfloat16* __restrict__ dx4,
+                                                          const __nv_bfloat16* __restrict__ dx8, __nv_bfloat16* __restrict__ dstem,
+                                                          int B, int H, int W) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int bw = W >> 3, bh = H >> 3;
+    if (wid >= B * bh * bw) return;
+    const int b = wid / (bh * bw), r = wid - b * bh * bw, by = r / bw, bx = r - by * bw;
+    const size_t base = ((static_cast<size_t>(b) * H + by * 8) * W + bx * 8) * 32 + lane;
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(stem) + base;
+    uint32_t* out = reinterpret_cast<uint32_t*>(dstem) + base;
+    // level-1 winners (2x2) for both channels of the pair
+    float v1[2][16];
+    int i1[2][16];
+#pragma unroll
+    for (int qy = 0; qy < 4; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < 4; ++qx) {
+            float a[2][4];
+            int id[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int py = qy * 2 + (k >> 1), px = qx * 2 + (k & 1);
+                const float2 f = unpack_bf16x2(__ldg(in + (static_cast<size_t>(py) * W + px) * 32));
+                a[0][k] = f.x; a[1][k] = f.y;
+                id[k] = py * 8 + px;
+            }
+            argmax2x2(a[0], id, v1[0][qy * 4 + qx], i1[0][qy * 4 + qx]);
+            argmax2x2(a[1], id, v1[1][qy * 4 + qx], i1[1][qy * 4 + qx]);
+        }
+    // gradients per channel: d4 (four 4x4 blocks) = sum of 4 duplicated channels, d8 = sum of 8
+    const int H4 = H >> 2, W4 = W >> 2;
+    float g4[2][4], g8[2];
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(dx4 + ((static_cast<size_t>(b) * H4 + by * 2 + sy) * W4 + bx * 2 + sx) * 256) + lane);
+            const float2 a = unpack_bf16x2(q.x), c = unpack_bf16x2(q.y), d = unpack_bf16x2(q.z), e = unpack_bf16x2(q.w);
+            g4[0][sy * 2 + sx] = a.x + a.y + c.x + c.y;
+            g4[1][sy * 2 + sx] = d.x + d.y + e.x + e.y;
+        }
+    {
+        const uint4* q8 = reinterpret_cast<const uint4*>(dx8 + ((static_cast<size_t>(b) * bh + by) * bw + bx) * 512) + lane * 2;
+        const uint4 q0 = __ldg(q8), q1 = __ldg(q8 + 1);
+        const uint32_t u0[4] = {q0.x, q0.y, q0.z, q0.w}, u1[4] = {q1.x, q1.y, q1.z, q1.w};
+        g8[0] = 0.f; g8[1] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f0 = unpack_bf16x2(u0[i]), f1 = unpack_bf16x2(u1[i]);
+            g8[0] += f0.x + f0.y;
+            g8[1] += f1.x + f1.y;
+        }
+    }
+    int i2[2][4], i3[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        float v2[4];
+#pragma unroll
+        for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx) {
+                float a[4];
+                int id[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int q = (sy * 2 + (k >> 1)) * 4 + sx * 2 + (k & 1);
+                    a[k] = v1[ch][q];
+                    id[k] = i1[ch][q];
+                }
+                argmax2x2(a, id, v2[sy * 2 + sx], i2[ch][sy * 2 + sx]);
+            }
+        float v3;
+        argmax2x2(v2, i2[ch], v3, i3[ch]);
+    }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        float ga = (i3[0] == k) ? g8[0] : 0.f, gb = (i3[1] == k) ? g8[1] : 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            ga += (i2[0][s] == k) ? g4[0][s] : 0.f;
+            gb += (i2[1][s] == k) ? g4[1][s] : 0.f;
+        }
+        out[(static_cast<size_t>(k >> 3) * W + (k & 7)) * 32] = pack_bf16x2(ga, gb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem backward (p2igan.py:79).  dy [B,H,W,64] bf16 ->
+//   dx [B,16,H,W] f32 : transposed grouped conv + the repeat_interleave(4) path
+//   dw [64,4,9]   f32 : sum_pix dy[pix][oc] * x[g*4+icl][pix + tap]   (register-tiled, atomics at the end)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
+                                                          float* __restrict__ dx, int H, int W) {
+    __shared__ float sw[64 * 36];
+    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int b = blockIdx.z >> 2, g = blockIdx.z & 3, yy = blockIdx.y;
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xx >= W) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int oy = yy - ky + 1;
+        if (oy < 0 || oy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ox = xx - kx + 1;
+            if (ox < 0 || ox >= W) continue;
+            const uint4* dp = reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * H + oy) * W + ox) * 64 + g * 16);
+            const uint4 u0 = __ldg(dp), u1 = __ldg(dp + 1);
+            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 f = unpack_bf16x2(uu[i]);
+                const float* w0 = sw + (g * 16 + 2 * i) * 36 + ky * 3 + kx;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    acc[ci] = fmaf(f.x, w0[ci * 9], acc[ci]);
+                    acc[ci] = fmaf(f.y, w0[36 + ci * 9], acc[ci]);
+                }
+                if (ky == 1 && kx == 1) {   // repeat_interleave: output channel oc feeds input channel oc/4
+                    acc[(2 * i) >> 2] += f.x;
+                    acc[(2 * i + 1) >> 2] += f.y;
+                }
+            }
+        }
+    }
+    const size_t HW = static_cast<size_t>(H) * W;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) dx[(static_cast<size_t>(b) * 16 + g * 4 + ci) * HW + static_cast<size_t>(yy) * W + xx] = acc[ci];
+}
+
+// thread = (pixel sub-stream s in 0..3, group g, output quad oq, input channel icl): 4 oc x 9 taps accumulators.
+__global__ void __launch_bounds__(256) stem_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                          float* __restrict__ dw, int B, int H, int W) {
+    __shared__ float sdw[64 * 36];
+    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sdw[i] = 0.f;
+    __syncthreads();
+    const int t = threadIdx.x;
+    const int icl = t & 3, oq = (t >> 2) & 3, g = (t >> 4) & 3, s = t >> 6;
+    const size_t HW = static_cast<size_t>(H) * W;
+    float acc[4][9];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[o][k] = 0.f;
+    const long long npix = static_cast<long long>(B) * HW;
+    for (long long p = static_cast<long long>(blockIdx.x) * 4 + s; p < npix; p += static_cast<long long>(gridDim.x) * 4) {
+        const int b = static_cast<int>(p / HW);
+        const int pix = static_cast<int>(p - b * HW), yy = pix / W, xx = pix - yy * W;
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(dy + p * 64 + g * 16 + oq * 4));
+        const float2 d01 = unpack_bf16x2(q.x), d23 = unpack_bf16x2(q.y);
+        const float d[4] = {d01.x, d01.y, d23.x, d23.y};
+        const float* xb = x + (static_cast<size_t>(b) * 16 + g * 4 + icl) * HW;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iy = yy + ky - 1, ix = xx + kx - 1;
+                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + static_cast<size_t>(iy) * W + ix) : 0.f;
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o][ky * 3 + kx] = fmaf(d[o], v, acc[o][ky * 3 + kx]);
+            }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(&sdw[((g * 16 + oq * 4 + o) * 4 + icl) * 9 + k], acc[o][k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_head_bwd(const float* dout, const float* out, const void* x, const float* w, void* dx, float* dw, int B,
+                            int H, int W, void* stream) {
+    P2I_CHECK_ARG(dout && out && x && w && dx && dw, "head_bwd: null pointer");
+    const long long npix = static_cast<long long>(B) * H * W;
+    long long blocks = (npix + 63) / 64;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    head_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+        dout, out, static_cast<const __nv_bfloat16*>(x), w, static_cast<__nv_bfloat16*>(dx), dw, npix, H * W);
+    P2I_CHECK_LAUNCH("head_bwd_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_upmod_bwd(const void* z, const float* pos, const float* bias, const void* dout, void* g_scratch, void* dz,
+                             float* dbias, float* dpos, int B, int h, int w, int C, void* stream) {
+    P2I_CHECK_ARG(z && pos && bias && dout && g_scratch && dz && dbias && dpos, "upmod_bwd: null pointer");
+    P2I_CHECK_ARG(C % 64 == 0 && (C & (C - 1)) == 0, "upmod_bwd: C=%d must be a power of two >= 64", C);
+    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upmod_bwd_hi_kernel<<<static_cast<unsigned>(blocks), 256, C * sizeof(float), as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), pos, bias, static_cast<const __nv_bfloat16*>(dout),
+        static_cast<__nv_bfloat16*>(g_scratch), dbias, dpos, B, h, w, C);
+    P2I_CHECK_LAUNCH("upmod_bwd_hi_kernel");
+    const long long tl = static_cast<long long>(B) * h * w * (C / 8);
+    upmod_bwd_lo_kernel<<<static_cast<unsigned>((tl + 255) / 256), 256, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(g_scratch), static_cast<__nv_bfloat16*>(dz), B, h, w, C);
+    P2I_CHECK_LAUNCH("upmod_bwd_lo_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx8, void* dstem, int B, int H, int W,
+                               void* stream) {
+    P2I_CHECK_ARG(stem && dx4 && dx8 && dstem, "pyramid_bwd: null pointer");
+    P2I_CHECK_ARG(H % 8 == 0 && W % 8 == 0, "pyramid_bwd: H, W must be multiples of 8");
+    const int warps = B * (H / 8) * (W / 8);
+    pyramid_bwd_kernel<<<cdiv(warps, 8), 256, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(stem), static_cast<const __nv_bfloat16*>(dx4), static_cast<const __nv_bfloat16*>(dx8),
+        static_cast<__nv_bfloat16*>(dstem), B, H, W);
+    P2I_CHECK_LAUNCH("pyramid_bwd_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W,
+                            void* stream) {
+    P2I_CHECK_ARG(dy && x && w && dx && dw, "stem_bwd: null pointer");
+    dim3 grid(cdiv(W, 128), H, B * 4);
+    stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
+    P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");
+    const long long npix = static_cast<long long>(B) * H * W;
+    long long blocks = (npix + 3) / 4;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    stem_bwd_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
+    P2I_CHECK_LAUNCH("stem_bwd_dw_kernel");
+    return P2I_OK;
+}

@@ -97,6 +97,14 @@ def require_cuda(*tensors):
                                "There is no CPU path." % t.device)
 
 
+def pack_do_grad_table(entries) -> bytes:
+    """Pack P2iDoGrad structs: 6 pointers + 2 ints (56 bytes each)."""
+    out = b""
+    for W, D, Dd, g, dW, dD, ch in entries:
+        out += struct.pack("<QQQQQQii", W, D, Dd, g, dW, dD, ch, 0)
+    return out
+
+
 def pack_do_table(entries) -> bytes:
     """Pack P2iDoLayer structs: 5 pointers + 2 ints (48 bytes each)."""
     out = b""

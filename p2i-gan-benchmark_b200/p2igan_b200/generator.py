@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import pack_do_table, require_cuda
+from ._lib import pack_do_grad_table, pack_do_table, require_cuda
 from .layers import (BaseNetwork, BasicConv_do, DownsampleDuplicateChannels, EBlock, InputBlock, ResBlock_do, UPPos)
 
 
@@ -65,12 +65,12 @@ class P2IGenerator(BaseNetwork):
         """bf16 GEMM operands for all convs; recomposed only when a parameter changed (version counters)."""
         convs = list(self._res_convs())
         dev = convs[0][1].W.device
-        ptr_key = tuple(c.W.data_ptr() for _, c in convs) + tuple(c.D.data_ptr() for _, c in convs) + (need_dgrad,)
+        ptr_key = tuple(c.W.data_ptr() for _, c in convs) + tuple(c.D.data_ptr() for _, c in convs)
         ver_key = tuple(c.W._version for _, c in convs) + tuple(c.D._version for _, c in convs) + \
             tuple(u.proj.weight._version for u in self.UP) + (self.Convsin[0].main[0].W._version,
                                                              self.Convsin[0].main[0].D._version)
         wc = self._wcache
-        if wc is None or wc["ptr_key"] != ptr_key:
+        if wc is None or wc["ptr_key"] != ptr_key or (need_dgrad and wc["bufs_t"][0] is None):
             bufs = [torch.empty(9, c.in_channels, c.in_channels, dtype=torch.bfloat16, device=dev) for _, c in convs]
             bufs_t = [torch.empty_like(b) for b in bufs] if need_dgrad else [None] * len(bufs)
             tab = pack_do_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), b.data_ptr(),
@@ -84,6 +84,7 @@ class P2IGenerator(BaseNetwork):
             s = self.Convsin[0].main[0]
             wc["stem"] = ops.doconv_compose_stem(s.W.detach(), s.D.detach(), s.D_diag.detach())
             wc["up"] = [u.proj_weight_cl() for u in self.UP]
+            wc["up_t"] = [w.transpose(1, 2).contiguous() for w in wc["up"]]
             wc["ver_key"] = ver_key
         return wc
 
@@ -116,10 +117,154 @@ class P2IGenerator(BaseNetwork):
         b, t, c, h, w = masked_frames.shape
         if (t * c, h, w) != (16, self.H, self.W):
             raise ValueError(f"P2IGenerator built for 16x{self.H}x{self.W}, got {t * c}x{h}x{w}")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("P2IGenerator: training (autograd) path is not built yet; call under torch.no_grad()")
         mf = masked_frames.reshape(b, c * t, h, w)
         mk = masks.reshape(b, c * t, h, w)
-        x = self.input(mf, mk)
-        out = self.trunk_cl(x, self._weights())
+        params = [p for _, p in self.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            out = _GeneratorFn.apply(self, mf, mk, *params)
+        else:
+            x = self.input(mf, mk)
+            out = self.trunk_cl(x, self._weights())
         return out.view(b, t, c, h, w)
+
+    # ------------------------------------------------------------------ training path
+    def _grad_table(self, wc: Dict):
+        """One fp32 wgrad arena for the 32 DO-Conv layers + the device table of the composition backward."""
+        convs = list(self._res_convs())
+        key = wc["ptr_key"]
+        gt = getattr(self, "_gtable", None)
+        if gt is None or gt["key"] != key:
+            dev = convs[0][1].W.device
+            sizes = [9 * c.in_channels * c.in_channels for _, c in convs]
+            arena = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            views, o = [], 0
+            for n, (_, c) in zip(sizes, convs):
+                views.append(arena[o:o + n].view(9, c.in_channels, c.in_channels))
+                o += n
+            gt = {"key": key, "arena": arena, "views": views}
+            self._gtable = gt
+        return gt
+
+    def _forward_train(self, mf, mk):
+        """Forward that keeps what the backward needs. Returns (out f32 [B,16,H,W], saved dict)."""
+        wc = self._weights(need_dgrad=True)
+        bufs = wc["bufs"]
+        x_in, ictx = self.input.forward_ctx(mf, mk, save_for_backward=True)
+        sv = {"ictx": ictx, "x_in": x_in, "wc": wc, "res": {}, "up": {}}
+
+        def eblock(level, x):
+            base = level * 2 * self.num_res
+            acts = []
+            for r in range(self.num_res):
+                y = ops.conv2d_cl(x, bufs[base + 2 * r], None, True)
+                o = ops.conv2d_cl(y, bufs[base + 2 * r + 1], x, False)
+                acts.append((x, y))
+                x = o
+            sv["res"][level] = acts
+            return x
+
+        def up(i, x, skip=None):
+            U = self.UP[i]
+            z = ops.conv2d_cl(x, wc["up"][i])
+            pos = U.pos.detach().reshape(U.pos.shape[-2], U.pos.shape[-1]).contiguous()
+            bias = U.proj.bias.detach().contiguous()
+            sv["up"][i] = (x, z, pos, bias)
+            return ops.upmod_fwd(z, pos, bias, skip)
+
+        stem = ops.stem_fwd(x_in, wc["stem"])
+        x4, x8 = ops.pyramid_fwd(stem)
+        sv["stem"] = stem
+        r = eblock(3, x8)
+        r = up(2, r, skip=x4)
+        r = eblock(2, r)
+        r = up(1, r)
+        r = eblock(1, r)
+        r = up(0, r)
+        r = eblock(0, r)
+        w_out = self.ConvsOut[0].main[0].W.detach().reshape(16, 16).contiguous()
+        out = ops.head_fwd(r, w_out)
+        sv["r"], sv["w_out"], sv["out"] = r, w_out, out
+        return out, sv
+
+    def _backward_train(self, sv, dout):
+        """dout f32 [B,16,H,W] -> {parameter name: gradient}."""
+        wc = sv["wc"]
+        bufs_t = wc["bufs_t"]
+        gt = self._grad_table(wc)
+        gt["arena"].zero_()
+        gviews = gt["views"]
+        grads: Dict[str, torch.Tensor] = {}
+        d, dw_out = ops.head_bwd(dout.contiguous(), sv["out"], sv["r"], sv["w_out"])
+        grads["ConvsOut.0.main.0.W"] = dw_out.reshape(16, 16, 1)
+
+        def eblock_bwd(level, d):
+            base = level * 2 * self.num_res
+            for r in reversed(range(self.num_res)):
+                a, y = sv["res"][level][r]
+                ops.conv2d_wgrad(y, d, 3, out=gviews[base + 2 * r + 1])
+                dy = ops.conv2d_cl(d, bufs_t[base + 2 * r + 1], None, False, mask=y)
+                ops.conv2d_wgrad(a, dy, 3, out=gviews[base + 2 * r])
+                d = ops.conv2d_cl(dy, bufs_t[base + 2 * r], d, False)
+            return d
+
+        def up_bwd(i, d):
+            x, z, pos, bias = sv["up"][i]
+            dz, dbias, dpos = ops.upmod_bwd(z, pos, bias, d)
+            dwp = ops.conv2d_wgrad(x, dz, 1)
+            grads[f"UP.{i}.pos"] = dpos.reshape(1, 1, *dpos.shape)
+            grads[f"UP.{i}.proj.bias"] = dbias
+            grads[f"UP.{i}.proj.weight"] = dwp.reshape(dwp.shape[1], dwp.shape[2], 1, 1)
+            return ops.conv2d_cl(dz, wc["up_t"][i])
+
+        d = eblock_bwd(0, d)
+        d = up_bwd(0, d)
+        d = eblock_bwd(1, d)
+        d = up_bwd(1, d)
+        d = eblock_bwd(2, d)
+        d_x4 = d
+        d = up_bwd(2, d)
+        d_x8 = eblock_bwd(3, d)
+        d_stem = ops.pyramid_bwd(sv["stem"], d_x4, d_x8)
+        dx_in, dw_stem = ops.stem_bwd(d_stem, sv["x_in"], wc["stem"])
+        s = self.Convsin[0].main[0]
+        dWs, dDs = ops.doconv_compose_stem_bwd(s.W.detach(), s.D.detach(), s.D_diag.detach(), dw_stem)
+        grads["Convsin.0.main.0.W"], grads["Convsin.0.main.0.D"] = dWs, dDs
+        # InputBlock
+        inp, pts, counts, src, table = sv["ictx"]
+        dvals = ops.idw_knn_bwd(dx_in, table, counts, src, pts.shape[1])
+        w0, b0, w1, b1 = (p.detach().contiguous() for p in self.input.gate_params())
+        dw0, db0, dw1, db1 = ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals)
+        grads["input.layers.0.conv.weight"], grads["input.layers.0.conv.bias"] = dw0, db0
+        grads["input.layers.1.conv.weight"], grads["input.layers.1.conv.bias"] = dw1, db1
+        # DO-Conv composition backward for the 32 ResBlock convs (one batched launch pair)
+        convs = list(self._res_convs())
+        names = []
+        for level in range(4):
+            for r in range(self.num_res):
+                for j in range(2):
+                    names.append(f"Decoder.{level}.layers.{r}.main.{j}.main.0")
+        outs = [(torch.empty_like(c.W), torch.empty_like(c.D)) for _, c in convs]
+        tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), dW.data_ptr(),
+                                   dD.data_ptr(), c.in_channels) for (_, c), g, (dW, dD) in zip(convs, gviews, outs)])
+        tab_dev = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
+        ops.doconv_compose_bwd(tab_dev, len(convs), max(c.in_channels for _, c in convs))
+        for n, (dW, dD) in zip(names, outs):
+            grads[n + ".W"], grads[n + ".D"] = dW, dD
+        return grads
+
+
+class _GeneratorFn(torch.autograd.Function):
+    """Whole-generator autograd node: forward and backward are chains of libp2i_sm100a kernels."""
+
+    @staticmethod
+    def forward(ctx, gen, mf, mk, *params):
+        out, sv = gen._forward_train(mf, mk)
+        ctx.gen, ctx.sv = gen, sv
+        ctx.names = [n for n, _ in gen.named_parameters()]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.gen._backward_train(ctx.sv, dout)
+        ctx.sv = None
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)

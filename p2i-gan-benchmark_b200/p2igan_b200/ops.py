@@ -79,7 +79,8 @@ def idw_knn_bwd(dout, table, counts, src, cap: int):
 
 # ------------------------------------------------------------------------------------------- convolutions
 def conv2d_cl(x: Tensor, w: Tensor, residual: Optional[Tensor] = None, relu: bool = False,
-              out: Optional[Tensor] = None, direct: bool = False) -> Tensor:
+              out: Optional[Tensor] = None, direct: bool = False, mask: Optional[Tensor] = None,
+              bias: Optional[Tensor] = None, leaky: bool = False) -> Tensor:
     """x [B,H,W,Cin] bf16, w [k*k,Cout,Cin] bf16 -> [B,H,W,Cout] bf16 (tcgen05 implicit GEMM)."""
     require_cuda(x, w)
     B, H, W, Cin = x.shape
@@ -90,7 +91,19 @@ def conv2d_cl(x: Tensor, w: Tensor, residual: Optional[Tensor] = None, relu: boo
     if out is None:
         out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=x.device)
     LIB.call("p2i_conv2d_direct_fwd" if direct else "p2i_conv2d_igemm_fwd", ptr(_chk(x, torch.bfloat16, "x")),
-             ptr(_chk(w, torch.bfloat16, "w")), ptr(residual), ptr(out), B, H, W, Cin, Cout, k, 1 if relu else 0, stream())
+             ptr(_chk(w, torch.bfloat16, "w")), ptr(residual), ptr(mask), ptr(bias), ptr(out), B, H, W, Cin, Cout, k,
+             (1 if relu else 0) | (2 if leaky else 0), stream())
+    return out
+
+
+def conv2d_wgrad(x: Tensor, dy: Tensor, ksize: int, out: Optional[Tensor] = None) -> Tensor:
+    """x [B,H,W,Cin] bf16, dy [B,H,W,Cout] bf16 -> dW f32 [k*k,Cout,Cin] (accumulated into `out` if given)."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    if out is None:
+        out = torch.zeros(ksize * ksize, Cout, Cin, dtype=torch.float32, device=x.device)
+    LIB.call("p2i_conv2d_wgrad", ptr(_chk(x, torch.bfloat16, "x")), ptr(_chk(dy, torch.bfloat16, "dy")), ptr(out), B, H, W,
+             Cin, Cout, ksize, stream())
     return out
 
 
@@ -155,3 +168,53 @@ def from_cl(x: Tensor) -> Tensor:
     y = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
     LIB.call("p2i_nhwc_bf16_to_nchw_f32", ptr(_chk(x, torch.bfloat16, "x")), ptr(y), B, C, H, W, stream())
     return y
+
+
+# ------------------------------------------------------------------------------------------- backward glue
+def head_bwd(dout: Tensor, out: Tensor, x: Tensor, w: Tensor):
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.zeros(16, 16, dtype=torch.float32, device=x.device)
+    LIB.call("p2i_head_bwd", ptr(_chk(dout, torch.float32, "dout")), ptr(_chk(out, torch.float32, "out")), ptr(x), ptr(w),
+             ptr(dx), ptr(dw), B, H, W, stream())
+    return dx, dw
+
+
+def upmod_bwd(z: Tensor, pos: Tensor, bias: Tensor, dout: Tensor):
+    """-> (dz [B,h,w,C] bf16, dbias f32 [C], dpos f32 [2h,2w])."""
+    B, h, w, C = z.shape
+    scratch = torch.empty_like(dout)
+    dz = torch.empty_like(z)
+    dbias = torch.zeros(C, dtype=torch.float32, device=z.device)
+    dpos = torch.zeros(2 * h, 2 * w, dtype=torch.float32, device=z.device)
+    LIB.call("p2i_upmod_bwd", ptr(z), ptr(_chk(pos, torch.float32, "pos")), ptr(_chk(bias, torch.float32, "bias")),
+             ptr(_chk(dout, torch.bfloat16, "dout")), ptr(scratch), ptr(dz), ptr(dbias), ptr(dpos), B, h, w, C, stream())
+    return dz, dbias, dpos
+
+
+def pyramid_bwd(stem: Tensor, dx4: Tensor, dx8: Tensor) -> Tensor:
+    B, H, W, C = stem.shape
+    d = torch.empty_like(stem)
+    LIB.call("p2i_pyramid_bwd", ptr(stem), ptr(_chk(dx4, torch.bfloat16, "dx4")), ptr(_chk(dx8, torch.bfloat16, "dx8")), ptr(d),
+             B, H, W, stream())
+    return d
+
+
+def stem_bwd(dy: Tensor, x: Tensor, w: Tensor):
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.zeros(64, 4, 9, dtype=torch.float32, device=x.device)
+    LIB.call("p2i_stem_bwd", ptr(_chk(dy, torch.bfloat16, "dy")), ptr(x), ptr(w), ptr(dx), ptr(dw), B, H, W, stream())
+    return dx, dw
+
+
+def doconv_compose_bwd(table_dev: Tensor, n_layers: int, max_channels: int) -> None:
+    LIB.call("p2i_doconv_compose_bwd", ptr(table_dev), n_layers, max_channels, stream())
+
+
+def doconv_compose_stem_bwd(W, D, D_diag, dDoW):
+    dW = torch.empty_like(W)
+    dD = torch.empty_like(D)
+    LIB.call("p2i_doconv_compose_stem_bwd", ptr(W), ptr(D), ptr(D_diag), ptr(_chk(dDoW, torch.float32, "dDoW")), ptr(dW),
+             ptr(dD), stream())
+    return dW, dD
