@@ -123,6 +123,25 @@ int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, con
 int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, const void* mask, const float* bias,
                           void* y, int B, int H, int W, int Cin, int Cout, int ksize, int flags, void* stream);
 
+/* General form used by the discriminator: 5-D activations [samples, T, H, W, C] (T = 1 for 2-D), temporal taps,
+ * k in {1,2,3} with explicit left padding, temporal stride, fused bias / residual / activation / gradient mask and
+ * the space-to-depth output modes that turn the reference's stride-2 convs (models/p2igan.py:123-139) into
+ * stride-1 k=2 convs.  Weights: bf16 [kt*k*k][Cout][Cin], tap index (kt*k + ky)*k + kx. */
+typedef struct P2iConvDesc {
+    int samples, T_in, T_out, H, W, Cin, Cout; /* H, W: output (= input) spatial size of the GEMM grid            */
+    int kt, ksize;                             /* temporal taps (1|3), spatial taps k (1|2|3)                      */
+    int pad, pad_t;                            /* x_in = x + kx - pad ; t_in = stride_t*t_out + kt - pad_t         */
+    int stride_t;                              /* 1 | 2                                                            */
+    int t_transposed;                          /* 1: data gradient of a temporal stride_t conv:
+                                                  t_in = (t_out + pad_t - kt)/stride_t when divisible, else skipped */
+    int act;                                   /* 0 none | 1 ReLU | 2 LeakyReLU(0.2)                               */
+    int mask_mode;                             /* 0 none | 1 zero where mask<=0 | 2 scale by 0.2 where mask<=0     */
+    int out_mode;                              /* 0 natural | 1 space-to-depth pack | 2 space-to-depth unpack      */
+} P2iConvDesc;
+int p2i_conv_igemm(const void* x, const void* w, const P2iConvDesc* desc, const void* residual, const void* mask,
+                   const float* bias, void* y, void* stream);
+int p2i_conv_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc* desc, void* stream);
+
 /* Weight gradient: dW[tap][co][ci] += sum_pix dy[pix][co] * x[pix+tap][ci]  (fp32 [k*k][Cout][Cin], atomically
  * accumulated: the caller zero-fills).  x [B,H,W,Cin], dy [B,H,W,Cout] bf16.  Cin in {64} or % 128 == 0. */
 int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B, int H, int W, int Cin, int Cout, int ksize,
@@ -164,6 +183,82 @@ int p2i_upmod_bwd(const void* z, const float* pos, const float* bias, const void
 int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx8, void* dstem, int B, int H, int W, void* stream);
 /* dy [B,H,W,64] bf16, x f32 [B,16,H,W], w f32 [64,4,9] -> dx f32 [B,16,H,W] (overwritten), dw f32 [64,4,9] accumulated. */
 int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Discriminator  (p2igan_bench/models/p2igan.py:115-173; C2/C3 layer.py:402-407)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct P2iSnLayer {
+    const float* W; /* weight_orig viewed as [rows = Cout][cols = Cin*kt*k*k] */
+    float* u;       /* weight_u [rows]  (updated in place when training)       */
+    float* v;       /* weight_v [cols]  (updated in place when training)       */
+    float* sigma;   /* out: u . (W v)                                          */
+    int rows, cols;
+} P2iSnLayer;
+/* torch.nn.utils.spectral_norm's pre-forward hook for a table of layers, one launch: training != 0 runs ONE
+ * power iteration (v <- normalize(W^T u), u <- normalize(W v), eps 1e-12) before sigma; eval uses stored u, v. */
+int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int training, void* stream);
+
+typedef struct P2iPackLayer {
+    const float* W;     /* weight_orig [Cout][Cin][kt][k][k]                                   */
+    const float* sigma; /* device scalar (NULL = 1)                                              */
+    void* out;          /* bf16 [taps'][Cout][Cin']  forward operand (may be NULL)               */
+    void* out_t;        /* bf16 [taps'][Cin'][Cout]  data-gradient operand, taps flipped (may be NULL) */
+    int Cout, Cin, KT, ksize;
+    int s2;             /* 1: spatial stride-2 layer -> k=2 taps over a space-to-depth input (Cin' = 4 Cin) */
+    int cin_pad;        /* Cin' for s2 == 0 (>= Cin; padded input channels stay zero)            */
+    int keep_t;         /* 1: do not flip temporal taps in out_t (temporally transposed dgrad)   */
+    int _pad;
+} P2iPackLayer;
+/* weight_orig / sigma -> bf16 GEMM operands for a table of layers (buffers zero-initialised once by the caller). */
+int p2i_disc_pack_weights(const P2iPackLayer* table_dev, int n_layers, void* stream);
+
+/* x f32 [B,C,H,W] -> bf16 [B,H,W,64], channels >= C zero (input of d2d.0). */
+int p2i_disc_pack_input(const float* x, void* y, int B, int C, int H, int W, void* stream);
+/* d3d.0: Conv3d(1->32, 3x3x3, stride (1,2,2), pad 1) + bias + LeakyReLU(0.2) -> bf16 space-to-depth
+ * [B,T,H/4,W/4,128].  x f32 [B,T,H,W]; w = weight_orig f32 [32,27], divided by *sigma in-kernel. */
+int p2i_d3d_first_fwd(const float* x, const float* w, const float* sigma, const float* bias, void* y, int B, int T, int H,
+                      int W, void* stream);
+/* d2d.8: Conv2d(C->1, 3x3, pad 1) + bias.  y bf16 [B,H,W,C]; w = weight_orig f32 [C,9]; out f32 [B,H,W]. */
+int p2i_d2d_last_fwd(const void* y, const float* w, const float* sigma, const float* bias, float* out, int B, int H, int W,
+                     int C, void* stream);
+/* d3d.8 (1x1x1, C->1) + mean over T + bilinear resize (align_corners=False) to [H2,W2] + sigmoid(alpha)*out2d fusion.
+ * z bf16 [B,T,h,w,C]; m_scratch f32 [B,h,w]; fused f32 [B,H2,W2]. */
+int p2i_disc_tail_fwd(const void* z, const float* w3, const float* sigma3, const float* b3, const float* out2d,
+                      const float* alpha, float* m_scratch, float* fused, int B, int T, int h, int w, int C, int H2, int W2,
+                      void* stream);
+
+/* ---- discriminator backward ---- */
+/* Tail backward.  dfused f32 [B,H2,W2] -> d_out2d f32 [B,H2,W2] (overwritten), dalpha (accumulated, may be NULL),
+ * dpre bf16 [B,T,h,w,C] = gradient w.r.t. the d3d.6 pre-activation (LeakyReLU mask of z applied), dW3 f32 [C] and
+ * db3 f32 [1] accumulated w.r.t. the NORMALISED 1x1x1 weight (may be NULL).  Requires H2 == 2h or H2 == h. */
+int p2i_disc_tail_bwd(const float* dfused, const float* out2d, const float* alpha, const void* z, const float* w3,
+                      const float* sigma3, float* d_out2d, float* dalpha, void* dpre, float* dW3, float* db3, int B, int T,
+                      int h, int w, int C, int H2, int W2, void* stream);
+/* d2d.8 backward: dpre bf16 [B,H,W,C] (LeakyReLU mask of y4 applied); dW f32 [C,9], db f32 [1] accumulated (may be NULL). */
+int p2i_d2d_last_bwd(const float* d_out, const void* y4, const float* w, const float* sigma, void* dpre, float* dW, float* db,
+                     int B, int H, int W, int C, void* stream);
+/* out[c] += sum_rows g[row][c]   (bias gradients; g bf16 [rows, C]). */
+int p2i_colsum_bf16(const void* g, float* out, long long rows, int C, void* stream);
+/* d3d.0 backward: dpre bf16 [B,T,H/2,W/2,32]; dW f32 [32,27] / db f32 [32] accumulated (both NULL to skip);
+ * dx f32 [B,T,H,W] overwritten (NULL to skip). */
+int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* w, const float* sigma, float* dW, float* db, float* dx,
+                      int B, int T, int H, int W, void* stream);
+/* dx[b,c,y,x] += g[b,y,x,c], c < C: adds the 2-D branch's (64-channel padded) input gradient to dx f32 [B,C,H,W]. */
+int p2i_disc_unpack_input_grad(const void* g, float* dx, int B, int C, int H, int W, void* stream);
+
+typedef struct P2iSnGrad {
+    const float* G;     /* dL/dW_sn: packed f32 [tap'][Cout][Cin'] (wgrad output) or plain [Cout][Cin*kt*k*k] */
+    const float* W;     /* weight_orig                                                                       */
+    const float* u;     /* u, v, sigma as used by the forward being differentiated                            */
+    const float* v;
+    const float* sigma;
+    float* dW;          /* out: gradient w.r.t. weight_orig, PyTorch layout                                   */
+    int Cout, Cin, KT, ksize;
+    int s2, cin_pad, packed, _pad;
+} P2iSnGrad;
+/* dW_orig = G/sigma - (<G, W_orig>/sigma^2) u v^T for a table of layers (spectral_norm backward with u, v detached). */
+int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses  (p2igan_bench/modules/losses.py:38-85, 192-253)

@@ -1,35 +1,46 @@
-// 2-D convolution (k in {1,3}, stride 1, zero pad k/2) as a tcgen05 implicit GEMM for sm_100a.
+// Convolution as a tcgen05 implicit GEMM for sm_100a: spatial stride 1, taps k in {1,2,3} (x KT in {1,3} frames).
 //
-//   reference call site: F.conv2d in DOConv2d._conv_forward (p2igan_bench/modules/deconv_pytorch.py:104-109)
-//   with the ReLU / residual of BasicConv_do / ResBlock_do fused (p2igan_bench/modules/layer.py:84-94,134-135),
-//   and the 1x1 projection of UPPos (layer.py:390,398).
+//   reference call sites
+//     F.conv2d in DOConv2d._conv_forward (p2igan_bench/modules/deconv_pytorch.py:104-109) with the ReLU /
+//       residual of BasicConv_do / ResBlock_do fused (p2igan_bench/modules/layer.py:84-94,134-135);
+//     the 1x1 projection of UPPos (layer.py:390,398);
+//     the spectral-norm Conv2d / Conv3d + LeakyReLU stacks of P2IDiscriminator (models/p2igan.py:120-142):
+//       their stride-2 convs run here as stride-1 k=2 convs on a space-to-depth input (out_mode 1 writes that
+//       layout for the next layer; out_mode 2 undoes it in the data-gradient pass), temporal taps are extra
+//       TMA coordinates (5-D tensor map [C, W, H, T, B]).
+//   The data gradient of every conv is this same kernel on dY with transposed, tap-flipped weights; the ReLU /
+//   LeakyReLU backward is fused as an output mask.
 //
-// GEMM view: M = B*H*W output pixels, N = Cout, K = k*k*Cin.
-//   A (activations) : NHWC bf16. One CTA tile = Ht x Wt = 128 output pixels of one image. For every
-//       64-channel block and every horizontal tap kx ONE TMA box of (Ht+k-1) x Wt pixels x 64 channels is
-//       loaded (out-of-image pixels are zero-filled by the TMA unit = the conv's zero padding). The k
-//       vertical taps reuse that box: tap ky starts ky*Wt rows further down, which is a multiple of
-//       1024 B because Wt % 8 == 0, so every shifted view is still a valid 128B-swizzled K-major
-//       UMMA operand. A is therefore fetched k (not k*k) times.
+// GEMM view: M = frames*H*W output pixels, N = Cout, K = KT*k*k*Cin.
+//   A (activations) : NHWC bf16. One CTA tile = Ht x Wt = 128 output pixels of one frame. For every temporal tap,
+//       64-channel block and horizontal tap kx ONE TMA box of (Ht+k-1) x Wt pixels x 64 channels is loaded
+//       (out-of-image pixels / frames are zero-filled by the TMA unit = the conv's zero padding). The k vertical
+//       taps reuse that box: tap ky starts ky*Wt rows further down, a multiple of 1024 B because Wt % 8 == 0, so
+//       every shifted view is still a valid 128B-swizzled K-major UMMA operand. A is fetched k (not k*k) times.
 //   B (weights)     : bf16 [tap][Cout][Cin] (K-major), one TMA box of NT x 64 per (tap, channel block).
 //   D (accumulator) : fp32 in TMEM, 128 lanes x NT columns, double buffered (2*NT <= 512 columns) so the
 //       epilogue of tile i overlaps the MMAs of tile i+1.
 // Warp roles (256 threads, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer (one elected
-// thread), warp2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> regs -> residual/ReLU -> bf16 -> global).
+// thread), warp2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> regs -> bias/residual/act/mask -> bf16 -> global).
 #include "common.h"
 #include "ptx.cuh"
 
 namespace p2i {
 
 struct ConvParams {
-    int B, H, W, Cin, Cout;
-    int KH, KW;
-    int Ht, Wt;
-    int tiles_x, tiles_y, m_tiles, total_tiles;
-    int relu;                          // 1 = ReLU, 2 = LeakyReLU(0.2)
-    const __nv_bfloat16* residual;     // added before the activation
-    const __nv_bfloat16* mask;         // output zeroed where mask <= 0 (ReLU backward fused into dgrad)
-    const float* bias;                 // per output channel, fp32
+    int F;                 // output frames = samples * T_out
+    int T_out, T_in;       // frames per sample (1, 1 for 2-D)
+    int H, W, Cin, Cout;
+    int KT, KH, KW;
+    int pad, pad_t, st;    // x_in = x + kx - pad ; t_in = st*t_out + kt - pad_t  (tmode 0)
+    int tmode;             // 1: transposed in t (dgrad of a temporal stride-st conv): t_in = (t_out + pad_t - kt)/st if divisible
+    int Ht, Wt, tiles_x, tiles_y, m_tiles, total_tiles;
+    int act;               // 0 none, 1 ReLU, 2 LeakyReLU(0.2)
+    int mask_mode;         // 0 none, 1: zero where mask <= 0, 2: x0.2 where mask <= 0
+    int out_mode;          // 0 natural [F,H,W,Cout]; 1 space-to-depth pack -> [F,H/2,W/2,4*Cout]; 2 unpack -> [F,2H,2W,Cout/4]
+    const __nv_bfloat16* residual;   // natural layout, added before the activation
+    const __nv_bfloat16* mask;       // natural layout
+    const float* bias;               // fp32 [Cout]
     __nv_bfloat16* y;
 };
 
@@ -43,6 +54,15 @@ struct ConvCfg {
     static constexpr int SMEM = 1024 + SA * A_STAGE + SB * B_STAGE + NBAR * 8 + 16;
     static constexpr int TMEM_COLS = 2 * NT;
 };
+
+// source frame of temporal tap kt for output frame t_out; -1 = tap skipped (transposed mode, parity mismatch)
+__device__ __forceinline__ int src_frame(const ConvParams& p, int t_out, int kt, bool& skip) {
+    skip = false;
+    if (p.tmode == 0) return p.st * t_out + kt - p.pad_t;
+    const int s = t_out + p.pad_t - kt;
+    if (s % p.st != 0) { skip = true; return 0; }
+    return s / p.st;   // negative / too large values are zero-filled by TMA (s < 0 with st == 2: s/st rounds to 0 only for s == -1, which is odd -> skipped)
+}
 
 template <int NT>
 __global__ void __launch_bounds__(256, 1)
@@ -93,20 +113,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-                const int b = mt / tiles_per_img, r = mt - b * tiles_per_img;
+                const int f = mt / tiles_per_img, r = mt - f * tiles_per_img;
+                const int smp = f / p.T_out, t_out = f - smp * p.T_out;
                 const int y0 = (r / p.tiles_x) * p.Ht, x0 = (r % p.tiles_x) * p.Wt;
-                for (int cb = 0; cb < cblocks; ++cb) {
-                    for (int kx = 0; kx < p.KW; ++kx) {
-                        mbar_wait(&emptyA[sa], pa ^ 1);
-                        mbar_expect_tx(&fullA[sa], a_bytes);
-                        tma_load_4d(sA + sa * Cfg::A_STAGE, &tmA, &fullA[sa], cb * 64, x0 + kx - (p.KW >> 1),
-                                    y0 - (p.KH >> 1), b);
-                        if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
-                        for (int ky = 0; ky < p.KH; ++ky) {
-                            mbar_wait(&emptyB[sb], pb ^ 1);
-                            mbar_expect_tx(&fullB[sb], Cfg::B_STAGE);
-                            tma_load_3d(sB + sb * Cfg::B_STAGE, &tmB, &fullB[sb], cb * 64, nt * NT, ky * p.KW + kx);
-                            if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                for (int kt = 0; kt < p.KT; ++kt) {
+                    bool skip;
+                    const int t_in = src_frame(p, t_out, kt, skip);
+                    if (skip) continue;
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        for (int kx = 0; kx < p.KW; ++kx) {
+                            mbar_wait(&emptyA[sa], pa ^ 1);
+                            mbar_expect_tx(&fullA[sa], a_bytes);
+                            tma_load_5d(sA + sa * Cfg::A_STAGE, &tmA, &fullA[sa], cb * 64, x0 + kx - p.pad, y0 - p.pad, t_in, smp);
+                            if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
+                            for (int ky = 0; ky < p.KH; ++ky) {
+                                mbar_wait(&emptyB[sb], pb ^ 1);
+                                mbar_expect_tx(&fullB[sb], Cfg::B_STAGE);
+                                tma_load_3d(sB + sb * Cfg::B_STAGE, &tmB, &fullB[sb], cb * 64, nt * NT,
+                                            (kt * p.KH + ky) * p.KW + kx);
+                                if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                            }
                         }
                     }
                 }
@@ -120,30 +146,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int it = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
+                const int mt = tile % p.m_tiles;
+                const int t_out = (mt / tiles_per_img) % p.T_out;
                 mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * NT;
                 uint32_t acc = 0;
-                for (int cb = 0; cb < cblocks; ++cb) {
-                    for (int kx = 0; kx < p.KW; ++kx) {
-                        mbar_wait(&fullA[sa], pa);
-                        const uint32_t a_base = smem_u32(sA + sa * Cfg::A_STAGE);
-                        for (int ky = 0; ky < p.KH; ++ky) {
-                            mbar_wait(&fullB[sb], pb);
-                            tc_fence_after();
-                            const uint32_t a_addr = a_base + ky * p.Wt * 128;
-                            const uint32_t b_addr = smem_u32(sB + sb * Cfg::B_STAGE);
+                for (int kt = 0; kt < p.KT; ++kt) {
+                    bool skip;
+                    (void)src_frame(p, t_out, kt, skip);
+                    if (skip) continue;
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        for (int kx = 0; kx < p.KW; ++kx) {
+                            mbar_wait(&fullA[sa], pa);
+                            const uint32_t a_base = smem_u32(sA + sa * Cfg::A_STAGE);
+                            for (int ky = 0; ky < p.KH; ++ky) {
+                                mbar_wait(&fullB[sb], pb);
+                                tc_fence_after();
+                                const uint32_t a_addr = a_base + ky * p.Wt * 128;
+                                const uint32_t b_addr = smem_u32(sB + sb * Cfg::B_STAGE);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024),
-                                          make_sw128_desc(b_addr + k * 32, 16, 1024), idesc, acc);
-                                acc = 1;
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024),
+                                              make_sw128_desc(b_addr + k * 32, 16, 1024), idesc, acc);
+                                    acc = 1;
+                                }
+                                umma_commit(&emptyB[sb]);
+                                if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
                             }
-                            umma_commit(&emptyB[sb]);
-                            if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                            umma_commit(&emptyA[sa]);
+                            if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
                         }
-                        umma_commit(&emptyA[sa]);
-                        if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
                     }
                 }
                 umma_commit(&tfull[as]);
@@ -157,11 +190,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-            const int b = mt / tiles_per_img, r = mt - b * tiles_per_img;
+            const int f = mt / tiles_per_img, r = mt - f * tiles_per_img;
             const int y = (r / p.tiles_x) * p.Ht + row / p.Wt;
             const int x = (r % p.tiles_x) * p.Wt + row % p.Wt;
             const bool valid = (y < p.H) && (x < p.W);
-            const size_t off = ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.Cout + nt * NT;
+            const size_t off = ((static_cast<size_t>(f) * p.H + y) * p.W + x) * p.Cout + nt * NT;   // natural
             mbar_wait(&tfull[as], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + as * NT + (static_cast<uint32_t>(ew * 32) << 16);
@@ -171,15 +204,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_ld16(t_addr + c, v);
                 tmem_ld_wait();
                 if (valid) {
-                    float f[16];
+                    float fv[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 16; ++i) fv[i] = __uint_as_float(v[i]);
                     if (p.bias != nullptr) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * NT + c);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float4 bv = __ldg(bp + i);
-                            f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
+                            fv[4 * i] += bv.x; fv[4 * i + 1] += bv.y; fv[4 * i + 2] += bv.z; fv[4 * i + 3] += bv.w;
                         }
                     }
                     if (p.residual != nullptr) {
@@ -189,34 +222,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float2 t = unpack_bf16x2(rr[i]);
-                            f[2 * i] += t.x;
-                            f[2 * i + 1] += t.y;
+                            fv[2 * i] += t.x;
+                            fv[2 * i + 1] += t.y;
                         }
                     }
-                    if (p.relu == 1) {
+                    if (p.act == 1) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-                    } else if (p.relu == 2) {
+                        for (int i = 0; i < 16; ++i) fv[i] = fmaxf(fv[i], 0.f);
+                    } else if (p.act == 2) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+                        for (int i = 0; i < 16; ++i) fv[i] = fv[i] > 0.f ? fv[i] : 0.2f * fv[i];
                     }
-                    if (p.mask != nullptr) {
+                    if (p.mask_mode != 0) {
                         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off + c);
                         uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
                         const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                        const float neg = (p.mask_mode == 2) ? 0.2f : 0.f;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float2 t = unpack_bf16x2(mm[i]);
-                            if (!(t.x > 0.f)) f[2 * i] = 0.f;
-                            if (!(t.y > 0.f)) f[2 * i + 1] = 0.f;
+                            if (!(t.x > 0.f)) fv[2 * i] *= neg;
+                            if (!(t.y > 0.f)) fv[2 * i + 1] *= neg;
                         }
                     }
                     uint4 o0, o1;
-                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                    uint4* op = reinterpret_cast<uint4*>(p.y + off + c);
+                    o0.x = pack_bf16x2(fv[0], fv[1]);   o0.y = pack_bf16x2(fv[2], fv[3]);
+                    o0.z = pack_bf16x2(fv[4], fv[5]);   o0.w = pack_bf16x2(fv[6], fv[7]);
+                    o1.x = pack_bf16x2(fv[8], fv[9]);   o1.y = pack_bf16x2(fv[10], fv[11]);
+                    o1.z = pack_bf16x2(fv[12], fv[13]); o1.w = pack_bf16x2(fv[14], fv[15]);
+                    size_t o = off + c;
+                    if (p.out_mode == 1) {          // pack: pixel (y,x), channel n -> [y/2][x/2][(y&1)*2+(x&1)][n]
+                        const int n = nt * NT + c;
+                        o = (((static_cast<size_t>(f) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) *
+                                p.Cout + n;
+                    } else if (p.out_mode == 2) {   // unpack: channel n = q*C + ch -> pixel (2y + q/2, 2x + q%2), channel ch
+                        const int C = p.Cout >> 2;
+                        const int n = nt * NT + c, q = n / C, ch = n - q * C;
+                        o = ((static_cast<size_t>(f) * (2 * p.H) + 2 * y + (q >> 1)) * (2 * p.W) + 2 * x + (q & 1)) * C + ch;
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.y + o);
                     op[0] = o0;
                     op[1] = o1;
                 }
@@ -249,7 +293,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 }
 
 // --------------------------------------------------------------------------------------------
-// CUDA-core direct convolution: same contract, used by tests to triage the tensor-core kernel.
+// CUDA-core direct convolution (2-D, natural layout): used by tests to triage the tensor-core kernel.
 // --------------------------------------------------------------------------------------------
 __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                    const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ mask,
@@ -284,45 +328,49 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
     }
 }
 
-}  // namespace p2i
-
-using namespace p2i;
-
-extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, const void* mask,
-                                    const float* bias, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
-                                    int flags, void* stream) {
-    P2I_CHECK_ARG(x && w && y, "conv2d_igemm: null pointer");
-    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_igemm: ksize %d unsupported (1 or 3)", ksize);
-    P2I_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape B=%d H=%d W=%d", B, H, W);
-    P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
-                  "conv2d_igemm: Cin=%d Cout=%d must be positive multiples of 64", Cin, Cout);
+static int run_igemm(const void* x, const void* w, const P2iConvDesc& d, const void* residual, const void* mask,
+                     const float* bias, void* y, void* stream) {
+    P2I_CHECK_ARG(x && w && y, "conv_igemm: null pointer");
+    P2I_CHECK_ARG(d.ksize >= 1 && d.ksize <= 3, "conv_igemm: ksize %d unsupported (1..3)", d.ksize);
+    P2I_CHECK_ARG(d.kt == 1 || d.kt == 3, "conv_igemm: kt %d unsupported (1 or 3)", d.kt);
+    P2I_CHECK_ARG(d.samples > 0 && d.H > 0 && d.W > 0 && d.T_in > 0 && d.T_out > 0, "conv_igemm: bad shape");
+    P2I_CHECK_ARG(d.Cin % 64 == 0 && d.Cout % 64 == 0 && d.Cin > 0 && d.Cout > 0,
+                  "conv_igemm: Cin=%d Cout=%d must be positive multiples of 64", d.Cin, d.Cout);
+    P2I_CHECK_ARG(d.stride_t == 1 || d.stride_t == 2, "conv_igemm: temporal stride %d unsupported", d.stride_t);
+    P2I_CHECK_ARG(d.out_mode >= 0 && d.out_mode <= 2 && d.mask_mode >= 0 && d.mask_mode <= 2, "conv_igemm: bad mode");
+    P2I_CHECK_ARG(d.mask_mode == 0 || mask, "conv_igemm: mask_mode set without a mask");
+    P2I_CHECK_ARG(d.out_mode != 1 || (d.H % 2 == 0 && d.W % 2 == 0), "conv_igemm: s2d pack needs even H, W");
+    P2I_CHECK_ARG(d.out_mode != 2 || (d.Cout % 256 == 0 || (d.Cout / 4) % 16 == 0), "conv_igemm: s2d unpack needs Cout/4 %% 16 == 0");
     ConvParams p;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-    p.KH = ksize; p.KW = ksize;
-    p.Wt = (W >= 16) ? 16 : 8;
+    p.F = d.samples * d.T_out; p.T_out = d.T_out; p.T_in = d.T_in;
+    p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout;
+    p.KT = d.kt; p.KH = d.ksize; p.KW = d.ksize;
+    p.pad = d.pad; p.pad_t = d.pad_t; p.st = d.stride_t; p.tmode = d.t_transposed;
+    p.Wt = (d.W >= 16) ? 16 : 8;
     p.Ht = 128 / p.Wt;
-    p.tiles_x = cdiv(W, p.Wt);
-    p.tiles_y = cdiv(H, p.Ht);
-    p.m_tiles = B * p.tiles_x * p.tiles_y;
-    p.relu = (flags & P2I_CONV_RELU) ? 1 : ((flags & P2I_CONV_LEAKY) ? 2 : 0);
+    p.tiles_x = cdiv(d.W, p.Wt);
+    p.tiles_y = cdiv(d.H, p.Ht);
+    p.m_tiles = p.F * p.tiles_x * p.tiles_y;
+    p.act = d.act; p.mask_mode = d.mask_mode; p.out_mode = d.out_mode;
     p.residual = static_cast<const __nv_bfloat16*>(residual);
     p.mask = static_cast<const __nv_bfloat16*>(mask);
     p.bias = bias;
     p.y = static_cast<__nv_bfloat16*>(y);
-    const int NT = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
-    p.total_tiles = p.m_tiles * (Cout / NT);
+    const int NT = (d.Cout % 256 == 0) ? 256 : ((d.Cout % 128 == 0) ? 128 : 64);
+    p.total_tiles = p.m_tiles * (d.Cout / NT);
 
     CUtensorMap tmA, tmB;
     {
-        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
-        const uint64_t strides[4] = {0, uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
-        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht + ksize - 1), 1};
-        int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr, true);
+        const uint64_t C = d.Cin, W = d.W, H = d.H, T = d.T_in;
+        const uint64_t dims[5] = {C, W, H, T, uint64_t(d.samples)};
+        const uint64_t strides[5] = {0, C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+        const uint32_t box[5] = {64, uint32_t(p.Wt), uint32_t(p.Ht + d.ksize - 1), 1, 1};
+        int rc = encode_tmap_bf16(&tmA, x, 5, dims, strides, box, nullptr, true);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {uint64_t(Cin), uint64_t(Cout), uint64_t(ksize * ksize)};
-        const uint64_t strides[3] = {0, uint64_t(Cin) * 2, uint64_t(Cout) * Cin * 2};
+        const uint64_t dims[3] = {uint64_t(d.Cin), uint64_t(d.Cout), uint64_t(d.kt * d.ksize * d.ksize)};
+        const uint64_t strides[3] = {0, uint64_t(d.Cin) * 2, uint64_t(d.Cout) * d.Cin * 2};
         const uint32_t box[3] = {64, uint32_t(NT), 1};
         int rc = encode_tmap_bf16(&tmB, w, 3, dims, strides, box, nullptr, true);
         if (rc) return rc;
@@ -331,6 +379,29 @@ extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* re
     if (NT == 256) return launch_conv<256>(tmA, tmB, p, st);
     if (NT == 128) return launch_conv<128>(tmA, tmB, p, st);
     return launch_conv<64>(tmA, tmB, p, st);
+}
+
+}  // namespace p2i
+
+using namespace p2i;
+
+extern "C" int p2i_conv_igemm(const void* x, const void* w, const P2iConvDesc* desc, const void* residual, const void* mask,
+                              const float* bias, void* y, void* stream) {
+    P2I_CHECK_ARG(desc, "conv_igemm: null descriptor");
+    return run_igemm(x, w, *desc, residual, mask, bias, y, stream);
+}
+
+extern "C" int p2i_conv2d_igemm_fwd(const void* x, const void* w, const void* residual, const void* mask,
+                                    const float* bias, void* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                                    int flags, void* stream) {
+    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_igemm: ksize %d unsupported (1 or 3)", ksize);
+    P2iConvDesc d;
+    d.samples = B; d.T_in = 1; d.T_out = 1; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout;
+    d.kt = 1; d.ksize = ksize; d.pad = ksize / 2; d.pad_t = 0; d.stride_t = 1; d.t_transposed = 0;
+    d.act = (flags & P2I_CONV_RELU) ? 1 : ((flags & P2I_CONV_LEAKY) ? 2 : 0);
+    d.mask_mode = mask ? 1 : 0;
+    d.out_mode = 0;
+    return run_igemm(x, w, d, residual, mask, bias, y, stream);
 }
 
 extern "C" int p2i_conv2d_direct_fwd(const void* x, const void* w, const void* residual, const void* mask,

@@ -20,8 +20,9 @@
 namespace p2i {
 
 struct WgradParams {
-    int B, H, W, Cin, Cout;
-    int KH, KW;
+    int F, T_out, T_in, H, W, Cin, Cout;   // F = samples * T_out frames of dY
+    int KT, KH, KW;
+    int pad, pad_t, st;                    // x_in = x + kx - pad ; t_in = st*t_out + kt - pad_t
     int Ht, Wt, tiles_x, tiles_y, pix_tiles;
     int ci_tiles, co_tiles, ksplit;
     int stacked;     // 1: Cin tile = 64 channels, two vertical taps per MMA
@@ -65,7 +66,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int ks = item % p.ksplit; item /= p.ksplit;
     const int cot = item % p.co_tiles; item /= p.co_tiles;
     const int cit = item % p.ci_tiles; item /= p.ci_tiles;
-    const int kx = item;
+    const int kx = item % p.KW;
+    const int kt = item / p.KW;
     const int ci_atoms = p.stacked ? 1 : 2;
     const int co_atoms = p.nt >> 6;
     const int ci0 = cit * (p.stacked ? 64 : 128), co0 = cot * p.nt;
@@ -79,15 +81,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (elect_one()) {
             uint32_t s = 0, ph = 0;
             for (int t = t_begin; t < t_end; ++t) {
-                const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+                const int f = t / tiles_per_img, r = t - f * tiles_per_img;
+                const int smp = f / p.T_out, t_out = f - smp * p.T_out;
+                const int t_in = p.st * t_out + kt - p.pad_t;      // out-of-range frames are zero-filled by TMA
                 const int y0 = (r / p.tiles_x) * p.Ht, x0 = (r % p.tiles_x) * p.Wt;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], stage_tx);
                 uint8_t* st = smem + s * WG_STAGE_BYTES;
                 for (int a = 0; a < ci_atoms; ++a)
-                    tma_load_4d(st + a * WG_X_ATOM, &tmX, &full[s], ci0 + a * 64, x0 + kx - (p.KW >> 1), y0 - (p.KH >> 1), b);
+                    tma_load_5d(st + a * WG_X_ATOM, &tmX, &full[s], ci0 + a * 64, x0 + kx - p.pad, y0 - p.pad, t_in, smp);
                 for (int a = 0; a < co_atoms; ++a)
-                    tma_load_4d(st + 2 * WG_X_ATOM + a * WG_Y_ATOM, &tmY, &full[s], co0 + a * 64, x0, y0, b);
+                    tma_load_5d(st + 2 * WG_X_ATOM + a * WG_Y_ATOM, &tmY, &full[s], co0 + a * 64, x0, y0, t_out, smp);
                 if (++s == WG_STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -133,7 +137,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 ky = g;
                 ci = ci0 + row;
             }
-            const int tap = ky * p.KW + kx;
+            const int tap = (kt * p.KH + ky) * p.KW + kx;
             float* dst = p.dW + (static_cast<size_t>(tap) * p.Cout + co0) * p.Cin + ci;
             const uint32_t t_addr = tmem_base + g * p.nt + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
@@ -157,24 +161,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 using namespace p2i;
 
-extern "C" int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B, int H, int W, int Cin, int Cout,
-                                int ksize, void* stream) {
-    P2I_CHECK_ARG(x && dy && dW, "conv2d_wgrad: null pointer");
-    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize %d unsupported", ksize);
-    P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "conv2d_wgrad: channels must be multiples of 64");
-    P2I_CHECK_ARG(Cin == 64 || Cin % 128 == 0, "conv2d_wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
+static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc& d, void* stream) {
+    P2I_CHECK_ARG(x && dy && dW, "conv_wgrad: null pointer");
+    P2I_CHECK_ARG(d.ksize >= 1 && d.ksize <= 3 && (d.kt == 1 || d.kt == 3), "conv_wgrad: taps unsupported");
+    const int Cin = d.Cin, Cout = d.Cout;
+    P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "conv_wgrad: channels must be multiples of 64");
+    P2I_CHECK_ARG(Cin == 64 || Cin % 128 == 0, "conv_wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
+    P2I_CHECK_ARG(Cin != 64 || d.ksize == 3 || d.ksize == 1, "conv_wgrad: Cin=64 supports k in {1,3}");
     WgradParams p;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = ksize; p.KW = ksize;
-    p.Wt = (W >= 16) ? 16 : 8;
+    p.F = d.samples * d.T_out; p.T_out = d.T_out; p.T_in = d.T_in;
+    p.H = d.H; p.W = d.W; p.Cin = Cin; p.Cout = Cout;
+    p.KT = d.kt; p.KH = d.ksize; p.KW = d.ksize; p.pad = d.pad; p.pad_t = d.pad_t; p.st = d.stride_t;
+    p.Wt = (d.W >= 16) ? 16 : 8;
     p.Ht = 128 / p.Wt;
-    p.tiles_x = cdiv(W, p.Wt);
-    p.tiles_y = cdiv(H, p.Ht);
-    p.pix_tiles = B * p.tiles_x * p.tiles_y;
+    p.tiles_x = cdiv(d.W, p.Wt);
+    p.tiles_y = cdiv(d.H, p.Ht);
+    p.pix_tiles = p.F * p.tiles_x * p.tiles_y;
     p.stacked = (Cin == 64) ? 1 : 0;
     p.nt = (Cout % 128 == 0) ? 128 : 64;
     p.ci_tiles = p.stacked ? 1 : Cin / 128;
     p.co_tiles = Cout / p.nt;
-    const int items = p.KW * p.ci_tiles * p.co_tiles;
+    const int items = p.KT * p.KW * p.ci_tiles * p.co_tiles;
     int ks = cdiv(sm_count(), items);
     if (ks > p.pix_tiles) ks = p.pix_tiles;
     if (ks < 1) ks = 1;
@@ -183,17 +190,19 @@ extern "C" int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B,
 
     CUtensorMap tmX, tmY;
     {
-        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(B)};
-        const uint64_t strides[4] = {0, uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
-        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht + ksize - 1), 1};
-        int rc = encode_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr, true);
+        const uint64_t C = Cin, W = d.W, H = d.H, T = d.T_in;
+        const uint64_t dims[5] = {C, W, H, T, uint64_t(d.samples)};
+        const uint64_t strides[5] = {0, C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+        const uint32_t box[5] = {64, uint32_t(p.Wt), uint32_t(p.Ht + d.ksize - 1), 1, 1};
+        int rc = encode_tmap_bf16(&tmX, x, 5, dims, strides, box, nullptr, true);
         if (rc) return rc;
     }
     {
-        const uint64_t dims[4] = {uint64_t(Cout), uint64_t(W), uint64_t(H), uint64_t(B)};
-        const uint64_t strides[4] = {0, uint64_t(Cout) * 2, uint64_t(W) * Cout * 2, uint64_t(H) * W * Cout * 2};
-        const uint32_t box[4] = {64, uint32_t(p.Wt), uint32_t(p.Ht), 1};
-        int rc = encode_tmap_bf16(&tmY, dy, 4, dims, strides, box, nullptr, true);
+        const uint64_t C = Cout, W = d.W, H = d.H, T = d.T_out;
+        const uint64_t dims[5] = {C, W, H, T, uint64_t(d.samples)};
+        const uint64_t strides[5] = {0, C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+        const uint32_t box[5] = {64, uint32_t(p.Wt), uint32_t(p.Ht), 1, 1};
+        int rc = encode_tmap_bf16(&tmY, dy, 5, dims, strides, box, nullptr, true);
         if (rc) return rc;
     }
     static bool configured = false;
@@ -205,4 +214,19 @@ extern "C" int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B,
     conv_wgrad_kernel<<<items * ks, 256, WG_SMEM, as_stream(stream)>>>(tmX, tmY, p);
     P2I_CHECK_LAUNCH("conv_wgrad_kernel");
     return P2I_OK;
+}
+
+extern "C" int p2i_conv_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc* desc, void* stream) {
+    P2I_CHECK_ARG(desc, "conv_wgrad: null descriptor");
+    return run_wgrad(x, dy, dW, *desc, stream);
+}
+
+extern "C" int p2i_conv2d_wgrad(const void* x, const void* dy, float* dW, int B, int H, int W, int Cin, int Cout,
+                                int ksize, void* stream) {
+    P2I_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize %d unsupported", ksize);
+    P2iConvDesc d;
+    d.samples = B; d.T_in = 1; d.T_out = 1; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout;
+    d.kt = 1; d.ksize = ksize; d.pad = ksize / 2; d.pad_t = 0; d.stride_t = 1; d.t_transposed = 0;
+    d.act = 0; d.mask_mode = 0; d.out_mode = 0;
+    return run_wgrad(x, dy, dW, d, stream);
 }

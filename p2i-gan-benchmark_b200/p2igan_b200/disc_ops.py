@@ -1,0 +1,168 @@
+"""Discriminator forward / backward as chains of libp2i_sm100a kernels (reference: models/p2igan.py:157-173).
+
+Layer plan for an input [B, T=16, 1, H, W] (the stride-2 convs of the reference run as stride-1 k=2 convs on a
+space-to-depth ("s2d") input, which the previous layer's epilogue writes directly):
+
+  2-D branch                                         3-D branch
+  pack x -> [B,H,W,64] (16 real channels)            d3d.0  1->32  (1,2,2)  CUDA cores   -> s2d [B,T,H/4,W/4,128]
+  d2d.0  16->64  s1  k3  -> s2d [B,H/2,W/2,256]      d3d.2  32->64 (1,2,2)  kt3 k2       -> s2d [B,T,H/8,W/8,256]
+  d2d.2  64->128 s2  k2  -> s2d [B,H/4,W/4,512]      d3d.4  64->128 (1,2,2) kt3 k2       -> [B,T,H/8,W/8,128]
+  d2d.4  128->256 s2 k2  -> [B,H/4,W/4,256]          d3d.6  128->128 (2,1,1) kt3 k3 st2  -> [B,T/2,H/8,W/8,128]
+  d2d.6  256->256 s1 k3  -> [B,H/4,W/4,256]          d3d.8  128->1 1x1x1 + mean_t + bilinear resize   (tail kernel)
+  d2d.8  256->1   s1     -> [B,H/4,W/4] f32          fused = sigmoid(alpha2d) * out2d + resized        (tail kernel)
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+from typing import Dict, List, Optional
+
+import torch
+
+from ._lib import LIB, ptr, require_cuda, stream
+
+D2D = [0, 2, 4, 6, 8]
+D3D = [0, 2, 4, 6, 8]
+
+# (name, Cout, Cin, KT, ksize, s2, cin_pad, keep_t) for the tensor-core layers
+TC_LAYERS = [
+    ("d2d.0", 64, 16, 1, 3, 0, 64, 0),
+    ("d2d.2", 128, 64, 1, 3, 1, 0, 0),
+    ("d2d.4", 256, 128, 1, 3, 1, 0, 0),
+    ("d2d.6", 256, 256, 1, 3, 0, 256, 0),
+    ("d3d.2", 64, 32, 3, 3, 1, 0, 0),
+    ("d3d.4", 128, 64, 3, 3, 1, 0, 0),
+    ("d3d.6", 128, 128, 3, 3, 0, 128, 1),
+]
+ALL_SN = ["d2d.0", "d2d.2", "d2d.4", "d2d.6", "d2d.8", "d3d.0", "d3d.2", "d3d.4", "d3d.6", "d3d.8"]
+
+
+def conv_desc(samples, T_in, T_out, H, W, Cin, Cout, kt, ksize, pad, pad_t, stride_t=1, t_transposed=0, act=0, mask_mode=0,
+              out_mode=0):
+    """P2iConvDesc as a C int array (16 ints)."""
+    vals = [samples, T_in, T_out, H, W, Cin, Cout, kt, ksize, pad, pad_t, stride_t, t_transposed, act, mask_mode, out_mode]
+    return (ctypes.c_int * 16)(*vals)
+
+
+def conv_igemm(x, w, desc, residual=None, mask=None, bias=None, out=None):
+    LIB.call("p2i_conv_igemm", ptr(x), ptr(w), desc, ptr(residual), ptr(mask), ptr(bias), ptr(out), stream())
+    return out
+
+
+def conv_wgrad(x, dy, dW, desc):
+    LIB.call("p2i_conv_wgrad", ptr(x), ptr(dy), ptr(dW), desc, stream())
+    return dW
+
+
+def _mod(D, name):
+    seq, idx = name.split(".")
+    return getattr(D, seq)[int(idx)]
+
+
+class DiscState:
+    """Per-module cache: device tables, packed bf16 operands and sigma scalars."""
+
+    def __init__(self, D):
+        dev = D.alpha2d.device
+        self.dev = dev
+        self.sigma = torch.zeros(len(ALL_SN), dtype=torch.float32, device=dev)
+        mods = {n: _mod(D, n) for n in ALL_SN}
+        self.mods = mods
+        self.key = tuple(m.weight_orig.data_ptr() for m in mods.values())
+        sn = b""
+        for i, n in enumerate(ALL_SN):
+            m = mods[n]
+            rows = m.weight_orig.shape[0]
+            cols = m.weight_orig.numel() // rows
+            sn += struct.pack("<QQQQii", m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
+                              self.sigma[i:i + 1].data_ptr(), rows, cols)
+        self.sn_table = torch.frombuffer(bytearray(sn), dtype=torch.uint8).to(dev)
+        self.w: Dict[str, torch.Tensor] = {}
+        self.wt: Dict[str, torch.Tensor] = {}
+        pk = b""
+        for name, Cout, Cin, KT, k, s2, cin_pad, keep_t in TC_LAYERS:
+            taps = KT * (4 if s2 else k * k)
+            cinp = 4 * Cin if s2 else cin_pad
+            self.w[name] = torch.zeros(taps, Cout, cinp, dtype=torch.bfloat16, device=dev)
+            self.wt[name] = torch.zeros(taps, cinp, Cout, dtype=torch.bfloat16, device=dev)
+            si = ALL_SN.index(name)
+            pk += struct.pack("<QQQQiiiiiiii", mods[name].weight_orig.data_ptr(), self.sigma[si:si + 1].data_ptr(),
+                              self.w[name].data_ptr(), self.wt[name].data_ptr(), Cout, Cin, KT, k, s2, cinp, keep_t, 0)
+        self.pack_table = torch.frombuffer(bytearray(pk), dtype=torch.uint8).to(dev)
+
+    def sig(self, name):
+        i = ALL_SN.index(name)
+        return self.sigma[i:i + 1]
+
+
+def _state(D) -> DiscState:
+    st = getattr(D, "_p2i_state", None)
+    key = tuple(_mod(D, n).weight_orig.data_ptr() for n in ALL_SN)
+    if st is None or st.key != key:
+        st = DiscState(D)
+        D._p2i_state = st
+    return st
+
+
+def forward_ctx(D, x: torch.Tensor, save: bool = False):
+    """x [B,T,1,H,W] f32 -> (logits [B,(H/4)(W/4)] f32, ctx).  Runs the spectral-norm hook semantics first:
+    in train() mode every call performs one power iteration and updates weight_u / weight_v in place."""
+    require_cuda(x)
+    B, T, C, H, W = x.shape
+    if T * C != D.in_channels or T != 16:
+        raise ValueError(f"P2IDiscriminator expects {D.in_channels} frames, got {T * C}")
+    if H % 16 or W % 16:
+        raise ValueError("P2IDiscriminator requires H and W to be multiples of 16")
+    st = _state(D)
+    dev = x.device
+    xf = x.detach().reshape(B, T, H, W).contiguous().float()
+    LIB.call("p2i_spectral_norm", ptr(st.sn_table), len(ALL_SN), 1 if D.training else 0, stream())
+    LIB.call("p2i_disc_pack_weights", ptr(st.pack_table), len(TC_LAYERS), stream())
+    bf = torch.bfloat16
+    bias = {n: st.mods[n].bias.detach() for n in ALL_SN}
+    # ---- 2-D branch
+    a0 = torch.empty(B, H, W, 64, dtype=bf, device=dev)
+    LIB.call("p2i_disc_pack_input", ptr(xf), ptr(a0), B, 16, H, W, stream())
+    y1 = torch.empty(B, H // 2, W // 2, 256, dtype=bf, device=dev)
+    conv_igemm(a0, st.w["d2d.0"], conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0, act=2, out_mode=1), bias=bias["d2d.0"], out=y1)
+    y2 = torch.empty(B, H // 4, W // 4, 512, dtype=bf, device=dev)
+    conv_igemm(y1, st.w["d2d.2"], conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0, act=2, out_mode=1), bias=bias["d2d.2"], out=y2)
+    y3 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
+    conv_igemm(y2, st.w["d2d.4"], conv_desc(B, 1, 1, H // 4, W // 4, 512, 256, 1, 2, 1, 0, act=2), bias=bias["d2d.4"], out=y3)
+    y4 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
+    conv_igemm(y3, st.w["d2d.6"], conv_desc(B, 1, 1, H // 4, W // 4, 256, 256, 1, 3, 1, 0, act=2), bias=bias["d2d.6"], out=y4)
+    o2d = torch.empty(B, H // 4, W // 4, dtype=torch.float32, device=dev)
+    LIB.call("p2i_d2d_last_fwd", ptr(y4), ptr(st.mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")), ptr(bias["d2d.8"]),
+             ptr(o2d), B, H // 4, W // 4, 256, stream())
+    # ---- 3-D branch
+    z1 = torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev)
+    LIB.call("p2i_d3d_first_fwd", ptr(xf), ptr(st.mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")), ptr(bias["d3d.0"]),
+             ptr(z1), B, T, H, W, stream())
+    z2 = torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev)
+    conv_igemm(z1, st.w["d3d.2"], conv_desc(B, T, T, H // 4, W // 4, 128, 64, 3, 2, 1, 1, act=2, out_mode=1), bias=bias["d3d.2"], out=z2)
+    z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
+    conv_igemm(z2, st.w["d3d.4"], conv_desc(B, T, T, H // 8, W // 8, 256, 128, 3, 2, 1, 1, act=2), bias=bias["d3d.4"], out=z3)
+    T2 = (T + 2 - 3) // 2 + 1
+    z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
+    conv_igemm(z3, st.w["d3d.6"], conv_desc(B, T, T2, H // 8, W // 8, 128, 128, 3, 3, 1, 1, stride_t=2, act=2), bias=bias["d3d.6"], out=z4)
+    # ---- tail
+    m = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev)
+    fused = torch.empty(B, (H // 4) * (W // 4), dtype=torch.float32, device=dev)
+    LIB.call("p2i_disc_tail_fwd", ptr(z4), ptr(st.mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(bias["d3d.8"]),
+             ptr(o2d), ptr(D.alpha2d.detach()), ptr(m), ptr(fused), B, T2, H // 8, W // 8, 128, H // 4, W // 4, stream())
+    ctx = None
+    if save:
+        ctx = dict(xf=xf, a0=a0, y1=y1, y2=y2, y3=y3, y4=y4, o2d=o2d, z1=z1, z2=z2, z3=z3, z4=z4, m=m, dims=(B, T, H, W, T2),
+                   sigma=st.sigma.clone(), w={k: v.clone() for k, v in st.w.items()}, wt={k: v.clone() for k, v in st.wt.items()},
+                   u={n: st.mods[n].weight_u.detach().clone() for n in ALL_SN},
+                   v={n: st.mods[n].weight_v.detach().clone() for n in ALL_SN})
+    return fused, ctx
+
+
+def discriminator_forward(D, x):
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in D.parameters()))
+    if needs_grad:
+        from .disc_bwd import DiscriminatorFn
+        names = [n for n, _ in D.named_parameters()]
+        return DiscriminatorFn.apply(D, x, *[p for _, p in D.named_parameters()])
+    return forward_ctx(D, x)[0]

@@ -1,0 +1,124 @@
+"""GPU parity: P2IDiscriminator (spectral norm, 2-D + 3-D branches, fused tail) vs the CPU oracle.
+Tolerance: logits rel-L2 <= 3e-2 (bf16 activations), u/v/sigma fp32 abs 1e-5."""
+import pytest
+import torch
+
+import synth
+from oracle import p2i_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def _pair(H, W, seed=2024, perturb=True):
+    from p2igan_b200 import build_discriminator
+    torch.manual_seed(seed)
+    D = build_discriminator(synth.make_cfg(H, W))
+    if perturb:
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for n, p in D.named_parameters():
+                if n.endswith("bias") or n.startswith("alpha"):
+                    p.add_(torch.randn(p.shape, generator=g) * 0.1)
+    sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    return D.to(DEV), sd
+
+
+@pytest.mark.parametrize("H,W,B", [(32, 32, 2), (64, 64, 1), (128, 128, 1)])
+def test_discriminator_forward_train_mode(H, W, B):
+    D, sd = _pair(H, W)
+    frames, _, _ = synth.make_batch(B, 16, H, W, 12, 1)
+    D.train()
+    with torch.no_grad():
+        out1 = D(frames.to(DEV))
+        out2 = D((frames * 0.5).to(DEV))       # second call: second power iteration on the updated u/v
+    torch.cuda.synchronize()
+    ref1 = O.discriminator_forward(sd, frames, training=True)
+    ref2 = O.discriminator_forward(sd, frames * 0.5, training=True)
+    assert out1.shape == ref1.shape
+    assert rel_l2(out1, ref1) < 3e-2
+    assert rel_l2(out2, ref2) < 3e-2
+    got = D.state_dict()
+    for k in sd:
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            assert float((got[k].cpu() - sd[k]).abs().max()) < 1e-5, k
+
+
+def test_discriminator_forward_eval_mode_and_golden(golden):
+    D, sd = _pair(32, 32, perturb=False)
+    frames, _, _ = synth.make_batch(2, 16, 32, 32, 12, 1)
+    D.train()
+    with torch.no_grad():
+        lt = D(frames.to(DEV))
+    D.eval()
+    u_before = D.state_dict()["d2d.6.weight_u"].clone()
+    with torch.no_grad():
+        le = D(frames.to(DEV))
+    assert torch.equal(u_before, D.state_dict()["d2d.6.weight_u"])     # eval: no power iteration
+    assert rel_l2(lt, golden["d32"]["logits_train"]) < 3e-2
+    assert rel_l2(le, golden["d32"]["logits_eval"]) < 3e-2
+
+
+def test_discriminator_rejects_bad_input():
+    D, _ = _pair(32, 32)
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            D(torch.zeros(1, 8, 1, 32, 32, device=DEV))
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            D(torch.zeros(1, 16, 1, 32, 32))
+
+
+@pytest.mark.parametrize("H,W,B", [(32, 32, 2), (64, 64, 1)])
+def test_discriminator_gradients_match_oracle_autograd(H, W, B):
+    """Parameter gradients (incl. spectral-norm backward) and input gradient of a hinge loss.
+    Yardstick as for the generator (bf16 gradient tensors): per-tensor rel-L2 <= 8e-2."""
+    D, sd = _pair(H, W)
+    frames, _, _ = synth.make_batch(B, 16, H, W, 12, 1)
+    x_ref = frames.clone().requires_grad_(True)
+    train = [k for k in sd if k.endswith("weight_orig") or k.endswith("bias") or k == "alpha2d"]
+    p = {k: (v.clone().requires_grad_(True) if k in train else v.clone()) for k, v in sd.items()}
+    out_ref = O.discriminator_forward(p, x_ref, training=True)
+    loss_ref = O.gan_loss(out_ref, True, "hinge", True) + 0.3 * (out_ref ** 2).mean()
+    g_ref = torch.autograd.grad(loss_ref, [p[k] for k in train] + [x_ref])
+    g_ref, gx_ref = dict(zip(train, g_ref[:-1])), g_ref[-1]
+
+    from p2igan_b200.losses import gan_loss
+    D.train()
+    x = frames.to(DEV).requires_grad_(True)
+    out = D(x)
+    loss = gan_loss(out, True, loss_type="hinge", is_disc=True) + 0.3 * (out ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) + 1e-3
+    bad = []
+    for n, prm in D.named_parameters():
+        if n == "alpha3d":
+            assert prm.grad is None
+            continue
+        r = rel_l2(prm.grad, g_ref[n])
+        if r > 8e-2:
+            bad.append((n, r))
+    r = rel_l2(x.grad, gx_ref)
+    if r > 8e-2:
+        bad.append(("input", r))
+    assert not bad, bad
+
+
+def test_discriminator_frozen_params_input_grad_only():
+    D, sd = _pair(32, 32)
+    frames, _, _ = synth.make_batch(2, 16, 32, 32, 12, 1)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    D.train()
+    x = frames.to(DEV).requires_grad_(True)
+    (-D(x).mean()).backward()
+    assert x.grad is not None and all(p.grad is None for p in D.parameters())
+    x_ref = frames.clone().requires_grad_(True)
+    (-O.discriminator_forward(dict(sd), x_ref, training=True).mean()).backward()
+    assert rel_l2(x.grad, x_ref.grad) < 8e-2
