@@ -280,6 +280,23 @@ int p2i_gan_loss_fwd(const float* logits, long long n, int mode, float label, fl
 int p2i_gan_loss_bwd(const float* logits, long long n, int mode, float label, const float* gscale, float scale,
                      float* dlogits, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser  (torch.optim.Adam as used by scripts/train.py:125-136)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct P2iAdamTensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long n;
+} P2iAdamTensor;
+/* One launch for a whole model.  chunks_dev: int pairs (tensor index, chunk index), chunk = p2i_adam_chunk_elems()
+ * elements.  step >= 1 (bias corrections are computed on the host).  grad_scale multiplies every gradient
+ * (1/world_size when the gradients hold a SUM over data-parallel ranks). */
+int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, void* stream);
+int p2i_adam_chunk_elems(void);
+
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);
 int p2i_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, void* stream);

@@ -173,3 +173,70 @@ def test_generator_gradients_match_oracle_autograd(H, W, B, n_obs):
         if r > 8e-2:
             bad.append((n, r))
     assert not bad, bad[:8]
+
+
+def test_fused_adam_matches_torch_adam():
+    from p2igan_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(7,), (64, 4, 9), (300000,), (1,)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    a = [p.clone().to(DEV).requires_grad_(True) for p in ps]
+    b = [p.clone().requires_grad_(True) for p in ps]
+    oa, ob = FusedAdam(a, lr=1e-2, betas=(0.0, 0.99)), torch.optim.Adam(b, lr=1e-2, betas=(0.0, 0.99))
+    for it in range(3):
+        for x, y in zip(a, b):
+            gr = torch.randn(y.shape, generator=g)
+            x.grad, y.grad = gr.to(DEV), gr.clone()
+        oa.step(); ob.step()
+    for x, y in zip(a, b):
+        assert float((x.detach().cpu() - y.detach()).abs().max()) < 1e-6
+    sd = oa.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}          # torch.optim.Adam layout
+
+
+def test_gan_train_step_matches_oracle_and_reference_golden(golden):
+    """Two full G+D iterations (B=2, 32x32) in train.py's order vs the oracle step and the reference's own losses.
+    Losses are fp32 reductions of bf16-path activations: rel 3e-2 (rec/dis/adv). Parameters after 2 Adam steps move
+    by ~lr=1e-4 per element: compare the UPDATE direction via the oracle's parameters, abs 2.5e-4."""
+    from p2igan_b200 import build_discriminator, build_generator
+    from p2igan_b200.train_step import GANTrainStep
+    cfg = synth.make_cfg(32, 32)
+    torch.manual_seed(2024)
+    G, D = build_generator(cfg), build_discriminator(cfg)
+    g_sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    g_init = {k: v.clone() for k, v in g_sd.items()}
+    d_init = {k: v.clone() for k, v in d_sd.items()}
+    G, D = G.to(DEV).train(), D.to(DEV).train()
+    ts = GANTrainStep(cfg, G, D)
+    og, od = {}, {}
+    for it in range(2):
+        fr, mf, mk = synth.make_batch(2, 16, 32, 32, 12, 100 + it)
+        ours = {k: float(v) for k, v in ts.step(fr.to(DEV), mf.to(DEV), mk.to(DEV)).items()}
+        ref = O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it + 1, idw="exact")
+        gold = golden["train32"]["steps"][it]
+        for k in ("rec", "pool", "dis"):
+            assert abs(ours[k] - ref[k]) < 3e-2 * abs(ref[k]) + 1e-4, (it, k, ours[k], ref[k])
+            assert abs(ours[k] - gold[k]) < 6e-2 * abs(gold[k]) + 1e-4, (it, k, ours[k], gold[k])
+        assert abs(ours["adv"] - ref["adv"]) < 2e-3, (it, ours["adv"], ref["adv"])
+    # Adam with beta1 = 0 takes ~lr-sized sign-like steps, so elements whose gradient is at the bf16 noise floor may
+    # move in opposite directions (bounded by 2 steps x 2.41e-4); the UPDATE as a whole must point the same way.
+    def update_cosine(model, init, ref, skip=()):
+        got = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        num = da = db = 0.0
+        for k in init:
+            if any(k.endswith(s_) for s_ in skip):
+                continue
+            a_, b_ = (got[k] - init[k]).double(), (ref[k] - init[k]).double()
+            assert float((got[k] - ref[k]).abs().max()) <= 4.9e-4, k
+            num += float((a_ * b_).sum()); da += float((a_ * a_).sum()); db += float((b_ * b_).sum())
+        return num / max((da * db) ** 0.5, 1e-30), got
+    cg, got = update_cosine(G, g_init, g_sd, skip=("D_diag",))
+    cd, gotd = update_cosine(D, d_init, d_sd, skip=("weight_u", "weight_v", "alpha3d"))
+    assert cg > 0.85 and cd > 0.85, (cg, cd)
+    for k in g_sd:
+        if k.endswith("D_diag"):
+            assert torch.equal(got[k], g_sd[k])
+    for k in d_sd:
+        if k.endswith("_u") or k.endswith("_v"):
+            assert float((gotd[k] - d_sd[k]).abs().max()) < 1e-3, k
