@@ -130,30 +130,129 @@ def cpu_generator_events_per_s(n_events: int, steps: int, warmup: int):
     return n_events * steps / dt, cores, dt / steps
 
 
+def cpu_train_events_per_s(n_events: int, steps: int, warmup: int):
+    """Oracle GAN training step (scripts/train.py order: G fwd, rec loss, D x2, D Adam, D(G), G bwd, G Adam) on the host."""
+    from oracle import p2i_oracle as O
+    from p2igan_b200 import build_discriminator, build_generator
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    torch.manual_seed(2024)
+    cfg = synth.make_cfg(H, W)
+    g_sd = {k: v.detach().clone() for k, v in build_generator(cfg).state_dict().items()}
+    d_sd = {k: v.detach().clone() for k, v in build_discriminator(cfg).state_dict().items()}
+    og, od = {}, {}
+    fr, mf, mk = synth.make_batch(n_events, T, H, W, N_OBS, 1)
+    it = 0
+    for _ in range(warmup):
+        it += 1
+        O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it, idw="ref")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        it += 1
+        O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it, idw="ref")
+    dt = time.perf_counter() - t0
+    return n_events * steps / dt, cores, dt / steps
+
+
+WORKLOADS = {
+    "train": ("train events/s (G+D step, 16x128x128)",
+              "full GAN training step (generator + dual-branch patch discriminator, weighted-L1 + temporal-KL + hinge, "
+              "2x Adam) p2igan_gan_baseline.json, batch 16/GPU, synthetic events 16x128x128 (BASELINE configs[2])"),
+    "infer": ("infer events/s (generator forward, 16x128x128)",
+              "P2IGAN generator-only inference, batch 32 synthetic radar-input events 16x128x128 (BASELINE configs[1])"),
+}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_events = 2
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    v, cores, spp = cpu_generator_events_per_s(n_events, steps, warmup)
-    line = {"impl": "reference", "metric": "infer events/s (generator forward, 16x128x128)", "value": v, "unit": "events/s",
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    fn = cpu_train_events_per_s if args.workload == "train" else cpu_generator_events_per_s
+    v, cores, spp = fn(n_events, steps, warmup)
+    metric, wl = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": "events/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spp * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "P2IGAN generator-only inference, synthetic radar-input events 16x128x128 (BASELINE configs[1])",
-                       "events_per_step": n_events, "gauge_pixels": N_OBS},
+            "config": {"workload": wl, "events_per_step": n_events, "gauge_pixels": N_OBS},
             "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_events} events/step x {steps} steps of the same workload (oracle/p2i_oracle.py, "
-                                       "torch CPU fp32, reference-style cdist/topk IDW)"},
+                             "sample": f"{n_events} events/step x {steps} steps of the same workload (oracle/p2i_oracle.py: "
+                                       "torch CPU fp32 restatement of the reference, reference-style cdist/topk IDW)"},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+class ConvTimer:
+    """CUDA events around every tensor-core conv launch (forward / dgrad: conv_igemm_kernel; wgrad: conv_wgrad_kernel)
+    with the ALGORITHMIC FLOPs of each launch (space-to-depth k=2 layers count 9/16 of the executed MACs, the
+    channel-padded first 2-D discriminator layer 16/64)."""
+
+    def __init__(self):
+        self.ev = {"igemm": [], "wgrad": []}
+        self.flops = {"igemm": 0.0, "wgrad": 0.0}
+
+    def _rec(self, kind, fl, fn, *a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*a, **k)
+        e.record()
+        self.ev[kind].append((s, e))
+        self.flops[kind] += fl
+        return r
+
+    def install(self):
+        from p2igan_b200 import disc_bwd, disc_ops, ops
+        self._orig = (ops.conv2d_cl, ops.conv2d_wgrad, disc_ops.conv_igemm, disc_ops.conv_wgrad, disc_bwd.conv_igemm,
+                      disc_bwd.conv_wgrad)
+        o_cl, o_wg, d_ig, d_wg = self._orig[:4]
+
+        def cl(x, w, *a, **k):
+            B_, H_, W_, Cin = x.shape
+            return self._rec("igemm", 2.0 * B_ * H_ * W_ * w.shape[1] * Cin * w.shape[0], o_cl, x, w, *a, **k)
+
+        def wg(x, dy, ks, *a, **k):
+            B_, H_, W_, Cin = x.shape
+            return self._rec("wgrad", 2.0 * B_ * H_ * W_ * dy.shape[3] * Cin * ks * ks, o_wg, x, dy, ks, *a, **k)
+
+        def dfl(desc):
+            smp, Tin, Tout, H_, W_, Cin, Cout, kt, k = [desc[i] for i in range(9)]
+            f = 2.0 * smp * Tout * H_ * W_ * Cout * Cin * kt * k * k
+            if k == 2:
+                f *= 9.0 / 16.0
+            if kt == 1 and k == 3 and Cin == 64 and Cout == 64:
+                f *= 16.0 / 64.0
+            return f
+
+        def dig(x, w, desc, *a, **k):
+            return self._rec("igemm", dfl(desc), d_ig, x, w, desc, *a, **k)
+
+        def dwg(x, dy, dW, desc):
+            return self._rec("wgrad", dfl(desc), d_wg, x, dy, dW, desc)
+
+        ops.conv2d_cl, ops.conv2d_wgrad = cl, wg
+        disc_ops.conv_igemm, disc_ops.conv_wgrad = dig, dwg
+        disc_bwd.conv_igemm, disc_bwd.conv_wgrad = dig, dwg
+
+    def remove(self):
+        from p2igan_b200 import disc_bwd, disc_ops, ops
+        ops.conv2d_cl, ops.conv2d_wgrad, disc_ops.conv_igemm, disc_ops.conv_wgrad, disc_bwd.conv_igemm, disc_bwd.conv_wgrad = self._orig
+
+    def result(self):
+        torch.cuda.synchronize()
+        out = {}
+        for k in ("igemm", "wgrad"):
+            ms = sum(s.elapsed_time(e) for s, e in self.ev[k])
+            out[k] = (ms, len(self.ev[k]), self.flops[k])
+        return out
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from p2igan_b200 import build_generator, ops
+    from p2igan_b200 import build_discriminator, build_generator
     from p2igan_b200._lib import LIB
+    from p2igan_b200.train_step import GANTrainStep, GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,26 +261,52 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = args.batch
+    train = args.workload == "train"
+    B = args.batch or (16 if train else 32)
+    cfg = synth.make_cfg(H, W)
 
     torch.manual_seed(2024)
-    G = build_generator(synth.make_cfg(H, W)).to(dev).eval()
-    # four rotating input batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
-    batches = []
-    for i in range(4):
-        frames, masked, masks = synth.make_batch(B, T, H, W, N_OBS, 1000 * rank + i)
-        batches.append((masked.to(dev), masks.to(dev)))
-    host = [(m.cpu().pin_memory(), k.cpu().pin_memory()) for m, k in batches[:2]]
+    G = build_generator(cfg).to(dev)
+    D = build_discriminator(cfg).to(dev) if train else None
+    if train:
+        G.train(); D.train()
+        ts = GANTrainStep(cfg, G, D)
+    else:
+        G.eval()
+    # four rotating batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
+    batches = [tuple(t.to(dev) for t in synth.make_batch(B, T, H, W, N_OBS, 1000 * rank + i)) for i in range(4)]
+    host = [tuple(t.cpu().pin_memory() for t in b) for b in batches[:2]]
     out_host = torch.empty(B, T, 1, H, W, dtype=torch.float32).pin_memory()
+    loss_host = torch.empty(6, dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    def eager(fr, mf, mk):
+        if train:
+            o = ts.step(fr, mf, mk)
+            return torch.stack([o["rec"], o["pool"], o["reg"], o["adv"], o["dis"], o["total"]])
         with torch.no_grad():
-            return G(*batches[i % 4])
+            return G(mf, mk)
+
+    # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch
+    graphed = None if args.no_graph else GraphedStep(eager, batches[0], warmup=3)
+    run = graphed if graphed is not None else eager
+
+    def step(i):
+        return run(*batches[i % 4])
+
+    def e2e_step(i):
+        fr, mf, mk = host[i % 2]
+        if graphed is not None:          # H2D straight into the graph's static input buffers
+            for s_, t_ in zip(graphed.static_in, (fr, mf, mk)):
+                s_.copy_(t_, non_blocking=True)
+            o = graphed(*graphed.static_in)
+        else:
+            o = eager(fr.to(dev, non_blocking=True), mf.to(dev, non_blocking=True), mk.to(dev, non_blocking=True))
+        (loss_host if train else out_host).copy_(o, non_blocking=True)
 
     for i in range(max(3, args.warmup)):
         step(i)
@@ -201,15 +326,12 @@ def run_ours(args):
     barrier()
     t_wall1 = time.time()
     launches = LIB.launch_count() - l0
+    if graphed is not None:              # replays do not pass through the C entry points: count the captured launches
+        c0 = LIB.launch_count()
+        eager(*batches[0])
+        launches = (LIB.launch_count() - c0) * args.steps
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-
-    # ---- e2e: public API, pinned host inputs -> H2D, forward, D2H of the prediction, every step
-    def e2e_step(i):
-        m, k = host[i % 2]
-        with torch.no_grad():
-            o = G(m.to(dev, non_blocking=True), k.to(dev, non_blocking=True))
-        out_host.copy_(o, non_blocking=True)
 
     for i in range(2):
         e2e_step(i)
@@ -222,31 +344,14 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    # ---- dominant kernel: events around every tcgen05 conv launch of the same steps
-    conv_ms = 0.0
-    n_conv = 0
-    orig = ops.conv2d_cl
-    evs = []
-
-    def timed_conv(*a, **k):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(*a, **k)
-        e.record()
-        evs.append((s, e))
-        return r
-
-    ops.conv2d_cl = timed_conv
-    import p2igan_b200.layers as _layers
-    import p2igan_b200.generator as _gen
-    psteps = min(args.steps, 5)
+    # ---- dominant kernels: CUDA events around every tensor-core conv launch of the same steps
+    timer = ConvTimer()
+    timer.install()
+    psteps = min(args.steps, 4)
     for i in range(psteps):
-        step(i)
-    torch.cuda.synchronize()
-    ops.conv2d_cl = orig
-    for s, e in evs:
-        conv_ms += s.elapsed_time(e)
-    n_conv = len(evs)
+        eager(*batches[i % 4])           # eager replay of the same step so that per-launch events can be recorded
+    kt = timer.result()
+    timer.remove()
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -255,32 +360,43 @@ def run_ours(args):
     if rank == 0:
         sustained, burst, hbm, src = peaks()
         events = B * world * args.steps
-        value = events / (ms * 1e-3)
-        conv_tflops = (conv_flops_fwd(B) * psteps / (conv_ms * 1e-3)) / 1e12 if conv_ms > 0 else None
+        metric, wl = WORKLOADS[args.workload]
+        ig_ms, ig_n, ig_fl = kt["igemm"]
+        wg_ms, wg_n, wg_fl = kt["wgrad"]
+        ig_tf = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else None
+        wg_tf = wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None
+        if train:
+            h2d, d2h = 3 * B * T * H * W * 4, 6 * 4
+        else:
+            h2d, d2h = 2 * B * T * H * W * 4, B * T * H * W * 4
         line = {
-            "metric": "infer events/s (generator forward, 16x128x128)", "value": value, "unit": "events/s",
+            "metric": metric, "value": events / (ms * 1e-3), "unit": "events/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "P2IGAN generator-only inference, batch 32 synthetic radar-input events 16x128x128 "
-                                   "(BASELINE configs[1])", "events_per_step_per_gpu": B, "gauge_pixels": N_OBS,
-                       "weights": "random init seed 2024", "parallelism": f"events sharded over {world} GPU(s), no collective",
-                       "l2": "no explicit flush: 4 rotating input batches and a per-step working set (~2.6 GB of "
-                             "activations at B=32) far above the 126 MB L2"},
-            "e2e": {"value": events / (ms_e2e * 1e-3), "unit": "events/s",
-                    "h2d_bytes_per_step": 2 * B * T * H * W * 4, "d2h_bytes_per_step": B * T * H * W * 4},
+            "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS,
+                       "weights": "random init seed 2024", "launch": "eager" if graphed is None else "CUDA graph replay",
+                       "parallelism": (f"data parallel over {world} GPU(s): flat NCCL all-reduce of D and G gradients" if train
+                                       else f"events sharded over {world} GPU(s), no collective"),
+                       "l2": "no explicit flush: 4 rotating input batches and a per-step activation working set of several GB, "
+                             "far above the 126 MB L2"},
+            "e2e": {"value": events / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, 35 launches/step)",
-                         "achieved": conv_tflops, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": (conv_tflops / sustained) if conv_tflops else None, "traffic": None,
-                         "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
-                         "kernel_ms_per_step": conv_ms / max(psteps, 1), "launches_timed": n_conv},
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: forward + data-gradient launches)",
+                         "achieved": ig_tf, "peak": sustained, "unit": "TFLOP/s", "frac": (ig_tf / sustained) if ig_tf else None,
+                         "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "kernel_ms_per_step": ig_ms / psteps, "launches_per_step": ig_n // psteps,
+                         "algorithmic_gflop_per_step": ig_fl / psteps / 1e9,
+                         "wgrad_kernel": {"achieved": wg_tf, "frac": (wg_tf / sustained) if wg_tf else None,
+                                          "kernel_ms_per_step": wg_ms / psteps, "launches_per_step": wg_n // psteps,
+                                          "algorithmic_gflop_per_step": wg_fl / psteps / 1e9}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
-            v, cores, spp = cpu_generator_events_per_s(2, 3, 1)
+            fn = cpu_train_events_per_s if train else cpu_generator_events_per_s
+            v, cores, spp = fn(2, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                                    "sample": "2 events/step x 3 steps of the same workload (oracle/p2i_oracle.py, torch CPU "
-                                              "fp32, reference-style IDW)"}
+                                    "sample": "2 events/step x 2 steps of the same workload (oracle/p2i_oracle.py, torch CPU fp32 "
+                                              "restatement of the reference, reference-style IDW)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -291,9 +407,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="events per step per GPU")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=0, help="events per step per GPU (default 16 train / 32 infer)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -88,8 +88,8 @@ typedef struct P2iDoGrad {
     const float* D;      /* [C, 9, 9] */
     const float* D_diag; /* [C, 9, 9] */
     const float* dDoW;   /* f32 [9][C][C]: output of p2i_conv2d_wgrad */
-    float* dW;           /* [C, C, 9] (overwritten) */
-    float* dD;           /* [C, 9, 9] (overwritten) */
+    float* dW;           /* [C, C, 9] (accumulated: +=) */
+    float* dD;           /* [C, 9, 9] (accumulated: +=) */
     int channels;
     int _pad;
 } P2iDoGrad;
@@ -101,7 +101,7 @@ int p2i_doconv_compose_bwd(const P2iDoGrad* table_dev, int n_layers, int max_cha
 /* Grouped stem variant (Convsin: 16->64, k3, groups 4) keeping the reference's raw-reshape row
  * pairing (deconv_pytorch.py:119-124).  out f32 [64,4,9]. */
 int p2i_doconv_compose_stem_fwd(const float* W, const float* D, const float* D_diag, float* out, void* stream);
-/* dDoW f32 [64,4,9] -> dW [64,4,9], dD [16,9,9]. */
+/* dDoW f32 [64,4,9] -> dW [64,4,9], dD [16,9,9] (both accumulated: +=). */
 int p2i_doconv_compose_stem_bwd(const float* W, const float* D, const float* D_diag, const float* dDoW, float* dW,
                                 float* dD, void* stream);
 
@@ -193,6 +193,8 @@ typedef struct P2iSnLayer {
     float* u;       /* weight_u [rows]  (updated in place when training)       */
     float* v;       /* weight_v [cols]  (updated in place when training)       */
     float* sigma;   /* out: u . (W v)                                          */
+    float* u_snap;  /* optional copies of the u / v used for sigma (kept for the backward of THIS call, since */
+    float* v_snap;  /* the next forward updates weight_u / weight_v in place); may be NULL                    */
     int rows, cols;
 } P2iSnLayer;
 /* torch.nn.utils.spectral_norm's pre-forward hook for a table of layers, one launch: training != 0 runs ONE
@@ -253,12 +255,13 @@ typedef struct P2iSnGrad {
     const float* u;     /* u, v, sigma as used by the forward being differentiated                            */
     const float* v;
     const float* sigma;
-    float* dW;          /* out: gradient w.r.t. weight_orig, PyTorch layout                                   */
+    float* dW;          /* gradient w.r.t. weight_orig, PyTorch layout (accumulated: +=)                      */
     int Cout, Cin, KT, ksize;
     int s2, cin_pad, packed, _pad;
 } P2iSnGrad;
-/* dW_orig = G/sigma - (<G, W_orig>/sigma^2) u v^T for a table of layers (spectral_norm backward with u, v detached). */
-int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, void* stream);
+/* dW_orig = G/sigma - (<G, W_orig>/sigma^2) u v^T for a table of layers (spectral_norm backward with u, v detached).
+ * inner_scratch: f32 [n_layers], zero-filled by the caller. */
+int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, float* inner_scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses  (p2igan_bench/modules/losses.py:38-85, 192-253)
@@ -291,10 +294,10 @@ typedef struct P2iAdamTensor {
     long long n;
 } P2iAdamTensor;
 /* One launch for a whole model.  chunks_dev: int pairs (tensor index, chunk index), chunk = p2i_adam_chunk_elems()
- * elements.  step >= 1 (bias corrections are computed on the host).  grad_scale multiplies every gradient
- * (1/world_size when the gradients hold a SUM over data-parallel ranks). */
-int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float lr, float beta1, float beta2,
-                  float eps, int step, float grad_scale, void* stream);
+ * elements.  *step_dev (device float) is incremented first and drives the bias corrections, so the call is CUDA-graph
+ * capturable.  grad_scale multiplies every gradient (1/world_size when the gradients hold a SUM over ranks). */
+int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream);
 int p2i_adam_chunk_elems(void);
 
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */

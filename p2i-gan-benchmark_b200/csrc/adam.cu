@@ -6,20 +6,55 @@
 
 namespace p2i {
 
-constexpr int ADAM_CHUNK = 65536;
+constexpr int ADAM_CHUNK = 16384;
+
+__global__ void adam_tick_kernel(float* step) { *step += 1.f; }
 
 __global__ void __launch_bounds__(256) adam_kernel(const P2iAdamTensor* __restrict__ tensors, const int2* __restrict__ chunks,
-                                                   float lr_over_bc1, float inv_sqrt_bc2, float beta1, float beta2, float eps,
+                                                   const float* __restrict__ step_dev, float lr, float beta1, float beta2, float eps,
                                                    float grad_scale) {
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {                           // bias corrections from the device-resident step counter
+        const double st = static_cast<double>(*step_dev);
+        const double bc1 = 1.0 - pow(static_cast<double>(beta1), st), bc2 = 1.0 - pow(static_cast<double>(beta2), st);
+        s_c[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+        s_c[1] = static_cast<float>(1.0 / sqrt(bc2));
+    }
+    __syncthreads();
+    const float lr_over_bc1 = s_c[0], inv_sqrt_bc2 = s_c[1];
     const int2 ch = chunks[blockIdx.x];               // (tensor index, chunk index)
     const P2iAdamTensor t = tensors[ch.x];
     const long long start = static_cast<long long>(ch.y) * ADAM_CHUNK;
     const long long end = (start + ADAM_CHUNK < t.n) ? start + ADAM_CHUNK : t.n;
-    for (long long i = start + threadIdx.x; i < end; i += blockDim.x) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad) |
+                       reinterpret_cast<uintptr_t>(t.exp_avg) | reinterpret_cast<uintptr_t>(t.exp_avg_sq)) & 15) == 0;
+    const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+    long long i0 = start;
+    if (vec) {
+        const long long n4 = (end - start) >> 2;
+        float4* P = reinterpret_cast<float4*>(t.param + start);
+        const float4* Gd = reinterpret_cast<const float4*>(t.grad + start);
+        float4* M = reinterpret_cast<float4*>(t.exp_avg + start);
+        float4* V = reinterpret_cast<float4*>(t.exp_avg_sq + start);
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 p = P[i], g = Gd[i], m = M[i], v = V[i];
+            float* pp = &p.x; float* gp = &g.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gg = gp[k] * grad_scale;
+                mp[k] = mp[k] + (gg - mp[k]) * omb1;
+                vp[k] = vp[k] * beta2 + gg * gg * omb2;
+                pp[k] -= lr_over_bc1 * (mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps));
+            }
+            P[i] = p; M[i] = m; V[i] = v;
+        }
+        i0 = start + (n4 << 2);
+    }
+    for (long long i = i0 + threadIdx.x; i < end; i += blockDim.x) {
         const float g = t.grad[i] * grad_scale;
         float m = t.exp_avg[i], v = t.exp_avg_sq[i];
-        m = m + (g - m) * (1.f - beta1);              // lerp_
-        v = v * beta2 + g * g * (1.f - beta2);        // mul_().addcmul_()
+        m = m + (g - m) * omb1;                       // lerp_
+        v = v * beta2 + g * g * omb2;                 // mul_().addcmul_()
         const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
         t.param[i] -= lr_over_bc1 * (m / denom);
         t.exp_avg[i] = m;
@@ -29,13 +64,12 @@ __global__ void __launch_bounds__(256) adam_kernel(const P2iAdamTensor* __restri
 
 }  // namespace p2i
 
-extern "C" int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float lr, float beta1,
-                             float beta2, float eps, int step, float grad_scale, void* stream) {
-    P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step >= 1, "adam_step: bad arguments");
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-    p2i::adam_kernel<<<n_chunks, 256, 0, p2i::as_stream(stream)>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev),
-                                                                   static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)),
+extern "C" int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
+                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step_dev, "adam_step: bad arguments");
+    p2i::adam_tick_kernel<<<1, 1, 0, p2i::as_stream(stream)>>>(step_dev);
+    P2I_CHECK_LAUNCH("adam_tick_kernel");
+    p2i::adam_kernel<<<n_chunks, 256, 0, p2i::as_stream(stream)>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev), step_dev, lr,
                                                                    beta1, beta2, eps, grad_scale);
     P2I_CHECK_LAUNCH("adam_kernel");
     return P2I_OK;

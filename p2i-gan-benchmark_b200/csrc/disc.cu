@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(1024) spectral_norm_kernel(const P2iSnLayer* _
         __threadfence_block();
         __syncthreads();
     }
+    if (L.v_snap)
+        for (int j = threadIdx.x; j < K; j += blockDim.x) L.v_snap[j] = L.v[j];
     for (int i = warp; i < R; i += 32) {
         float s = 0.f;
         for (int j = lane; j < K; j += 32) s = fmaf(L.W[static_cast<size_t>(i) * K + j], L.v[j], s);
@@ -61,12 +63,16 @@ __global__ void __launch_bounds__(1024) spectral_norm_kernel(const P2iSnLayer* _
         for (int i = threadIdx.x; i < R; i += blockDim.x) {
             const float un = t2[i] / nrm;
             L.u[i] = un;
+            if (L.u_snap) L.u_snap[i] = un;
             dot += un * t2[i];
         }
         sigma = blk_sum(dot, sh);
     } else {
         float dot = 0.f;
-        for (int i = threadIdx.x; i < R; i += blockDim.x) dot += L.u[i] * t2[i];
+        for (int i = threadIdx.x; i < R; i += blockDim.x) {
+            dot += L.u[i] * t2[i];
+            if (L.u_snap) L.u_snap[i] = L.u[i];
+        }
         sigma = blk_sum(dot, sh);
     }
     if (threadIdx.x == 0) *L.sigma = sigma;

@@ -194,45 +194,58 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 //   dW[c][tap] += sum dpre * x_patch ; db[c] += sum dpre                     (one thread per output pixel)
 //   dx[b,t,y,x]  = sum_c sum_taps dpre[b, t-kt+1, (y-ky+1)/2, (x-kx+1)/2, c] * w[c][tap]/sigma   (gather, parity)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) d3d_first_bwd_w_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ x,
+// thread = (pixel sub-stream s in 0..15, channel octet cq in 0..3, temporal tap kt in 0..2): 8 channels x 9 spatial
+// taps accumulated in registers over the thread's pixels, one shared-memory + one global reduction per block.
+__global__ void __launch_bounds__(192) d3d_first_bwd_w_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ x,
                                                               float* __restrict__ dW, float* __restrict__ db, int B, int T, int H, int W) {
     __shared__ float sdw[32 * 27], sdb[32];
     for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) sdw[i] = 0.f;
     if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
     __syncthreads();
+    const int kt = threadIdx.x % 3, cq = (threadIdx.x / 3) & 3, s = threadIdx.x / 12;
     const int Ho = H >> 1, Wo = W >> 1;
     const long long total = static_cast<long long>(B) * T * Ho * Wo;
-    // thread (pixel stream, channel quad): 4 threads... simpler: each thread owns 8 channels of one pixel
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total * 4;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int cq = static_cast<int>(e & 3);
-        const long long idx = e >> 2;
+    float acc[8][9];
+    float bsum[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        bsum[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
+    }
+    for (long long idx = static_cast<long long>(blockIdx.x) * 16 + s; idx < total; idx += static_cast<long long>(gridDim.x) * 16) {
         const int xo = static_cast<int>(idx % Wo), yo = static_cast<int>((idx / Wo) % Ho);
         const int t = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % T), b = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho * T));
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(dpre + idx * 32 + cq * 8));
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
         float g[8];
-        bool any = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float2 f = unpack_bf16x2(qq[k]);
             g[2 * k] = f.x; g[2 * k + 1] = f.y;
-            any |= (f.x != 0.f) | (f.y != 0.f);
         }
-        if (!any) continue;
+        if (kt == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(&sdb[cq * 8 + k], g[k]);
-        for (int kt = 0; kt < 3; ++kt)
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ti = t + kt - 1, yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
-                    if (ti < 0 || ti >= T || yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
-                    const float v = __ldg(x + ((static_cast<size_t>(b) * T + ti) * H + yi) * W + xi);
-                    if (v == 0.f) continue;
-                    const int tap = (kt * 3 + ky) * 3 + kx;
+            for (int c = 0; c < 8; ++c) bsum[c] += g[c];
+        }
+        const int ti = t + kt - 1;
+        if (ti < 0 || ti >= T) continue;
+        const float* xp = x + (static_cast<size_t>(b) * T + ti) * H * W;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) atomicAdd(&sdw[(cq * 8 + k) * 27 + tap], g[k] * v);
-                }
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
+                const float v = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(xp + static_cast<size_t>(yi) * W + xi) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c][ky * 3 + kx] = fmaf(g[c], v, acc[c][ky * 3 + kx]);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(&sdw[(cq * 8 + c) * 27 + kt * 9 + k], acc[c][k]);
+        if (kt == 0) atomicAdd(&sdb[cq * 8 + c], bsum[c]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x)
@@ -309,23 +322,34 @@ __device__ __forceinline__ size_t packed_index(const P2iSnGrad& L, int co, int c
     return (static_cast<size_t>(tap) * L.Cout + co) * L.cin_pad + ci;
 }
 
-__global__ void __launch_bounds__(1024) sn_bwd_kernel(const P2iSnGrad* __restrict__ table) {
-    const P2iSnGrad L = table[blockIdx.x];
+constexpr int SN_BWD_BLOCKS = 32;   // blocks per layer
+// pass 1: inner[layer] += <G, W_orig>   pass 2: dW = G/sigma - inner/sigma^2 * u v^T
+__global__ void __launch_bounds__(256) sn_bwd_inner_kernel(const P2iSnGrad* __restrict__ table, float* __restrict__ inner) {
+    const P2iSnGrad L = table[blockIdx.y];
     __shared__ float sh[32];
     const int per = L.KT * L.ksize * L.ksize;
     const int K = L.Cin * per;
     const long long total = static_cast<long long>(L.Cout) * K;
     float acc = 0.f;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int r = static_cast<int>(e % per), ci = static_cast<int>((e / per) % L.Cin), co = static_cast<int>(e / K);
         acc += L.G[packed_index(L, co, ci, r)] * L.W[e];
     }
-    const float inner = blk_sum_all(acc, sh);
+    acc = blk_sum_all(acc, sh);
+    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(&inner[blockIdx.y], acc);
+}
+__global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const P2iSnGrad* __restrict__ table, const float* __restrict__ inner) {
+    const P2iSnGrad L = table[blockIdx.y];
+    const int per = L.KT * L.ksize * L.ksize;
+    const int K = L.Cin * per;
+    const long long total = static_cast<long long>(L.Cout) * K;
     const float sig = *L.sigma;
-    const float c1 = 1.f / sig, c2 = inner / (sig * sig);
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    const float c1 = 1.f / sig, c2 = inner[blockIdx.y] / (sig * sig);
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int r = static_cast<int>(e % per), ci = static_cast<int>((e / per) % L.Cin), co = static_cast<int>(e / K);
-        L.dW[e] = L.G[packed_index(L, co, ci, r)] * c1 - c2 * L.u[co] * L.v[e - static_cast<long long>(co) * K];
+        L.dW[e] += L.G[packed_index(L, co, ci, r)] * c1 - c2 * L.u[co] * L.v[e - static_cast<long long>(co) * K];
     }
 }
 
@@ -374,10 +398,10 @@ extern "C" int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* 
                                  float* dx, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dpre && x && w && sigma, "d3d_first_bwd: null pointer");
     if (dW && db) {
-        const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2) * 4;
-        long long blocks = (total + 127) / 128;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        d3d_first_bwd_w_kernel<<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dpre), x, dW,
+        const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
+        long long blocks = (total + 15) / 16;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        d3d_first_bwd_w_kernel<<<static_cast<unsigned>(blocks), 192, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dpre), x, dW,
                                                                                               db, B, T, H, W);
         P2I_CHECK_LAUNCH("d3d_first_bwd_w_kernel");
     }
@@ -399,9 +423,12 @@ extern "C" int p2i_disc_unpack_input_grad(const void* g, float* dx, int B, int C
     return P2I_OK;
 }
 
-extern "C" int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, void* stream) {
-    P2I_CHECK_ARG(table_dev && n_layers > 0, "spectral_norm_bwd: empty table");
-    sn_bwd_kernel<<<n_layers, 1024, 0, as_stream(stream)>>>(table_dev);
-    P2I_CHECK_LAUNCH("sn_bwd_kernel");
+extern "C" int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, float* inner_scratch, void* stream) {
+    P2I_CHECK_ARG(table_dev && n_layers > 0 && inner_scratch, "spectral_norm_bwd: bad arguments");
+    dim3 grid(SN_BWD_BLOCKS, n_layers);
+    sn_bwd_inner_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev, inner_scratch);
+    P2I_CHECK_LAUNCH("sn_bwd_inner_kernel");
+    sn_bwd_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev, inner_scratch);
+    P2I_CHECK_LAUNCH("sn_bwd_apply_kernel");
     return P2I_OK;
 }

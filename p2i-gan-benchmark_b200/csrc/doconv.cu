@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) doconv_bwd_w_kernel(const P2iDoGrad* __re
             float acc = 0.f;
 #pragma unroll
             for (int m = 0; m < 9; ++m) acc = fmaf(g[m], sD[ii][m * 9 + s], acc);
-            wp[s] = acc;
+            wp[s] += acc;
         }
     }
 }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) doconv_bwd_d_kernel(const P2iDoGrad* __re
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * 81; e += 256) {
         const int a = e / 81, r = e - a * 81;
-        L.dD[static_cast<size_t>(i0 + a) * 81 + r] = red[a][r];
+        L.dD[static_cast<size_t>(i0 + a) * 81 + r] += red[a][r];
     }
 }
 
@@ -162,14 +162,14 @@ __global__ void doconv_bwd_stem_kernel(const float* __restrict__ W, const float*
         float acc = 0.f;
 #pragma unroll
         for (int m = 0; m < 9; ++m) acc = fmaf(g[(oc * 4 + icl) * 9 + m], D[(i * 9 + m) * 9 + s] + Dd[(i * 9 + m) * 9 + s], acc);
-        dW[idx] = acc;
+        dW[idx] += acc;
     }
     if (idx < 16 * 81) {               // dD[i][m][s] = sum over (oc, icl) with (oc%4)*4+icl == i
         const int s = idx % 9, m = (idx / 9) % 9, i = idx / 81;
         const int icl = i % 4, r = i / 4;
         float acc = 0.f;
         for (int oc = r; oc < 64; oc += 4) acc = fmaf(g[(oc * 4 + icl) * 9 + m], W[(oc * 4 + icl) * 9 + s], acc);
-        dD[idx] = acc;
+        dD[idx] += acc;
     }
 }
 

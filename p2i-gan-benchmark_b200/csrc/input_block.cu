@@ -91,6 +91,7 @@ __global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const i
                                        const float* __restrict__ b1, float* __restrict__ vals,
                                        float* __restrict__ gate_l1, int HW) {
     __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
+    if (static_cast<int>(blockIdx.x * blockDim.x) >= counts[blockIdx.y]) return;   // no observed point in this block
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; }
     if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
     __syncthreads();
@@ -133,6 +134,7 @@ __global__ void gate_points_bwd_kernel(const float* __restrict__ masked, const i
                                        float* __restrict__ db1, int HW) {
     __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
     __shared__ float aw0[256], aw1[256], ab0[16], ab1[16];
+    if (static_cast<int>(blockIdx.x * blockDim.x) >= counts[blockIdx.y]) return;   // no observed point in this block
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; aw0[i] = 0.f; aw1[i] = 0.f; }
     if (threadIdx.x < 16) {
         sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x];
@@ -325,23 +327,41 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
     out[static_cast<size_t>(b) * Q + q] = r;
 }
 
-__global__ void idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
-                                      const float* __restrict__ nbr_w, const int* __restrict__ counts,
-                                      const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
+// dvals[b, idx] += w * dout.  Each block walks IDW_BWD_SPAN queries of one sample and privatises the scatter in
+// shared memory when the sample has at most IDW_SMEM_PTS points (one global atomic per touched point per block).
+constexpr int IDW_BWD_SPAN = 8192;
+__global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
+                                                             const float* __restrict__ nbr_w, const int* __restrict__ counts,
+                                                             const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
+    __shared__ float acc[IDW_SMEM_PTS];
     const int b = blockIdx.y;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q || counts[b] == 0) return;
-    const float g = dout[static_cast<size_t>(b) * Q + q];
-    if (g == 0.f) return;
+    const int N = counts[b];
+    if (N == 0) return;
+    const bool priv = N <= IDW_SMEM_PTS;
+    if (priv)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
     const int sb = src ? src[b] : b;
-    const size_t o = (static_cast<size_t>(sb) * Q + q) * 4;
-    const int4 id = __ldg(reinterpret_cast<const int4*>(nbr_idx + o));
-    const float4 w = __ldg(reinterpret_cast<const float4*>(nbr_w + o));
     float* v = dvals + static_cast<size_t>(b) * cap;
-    if (w.x != 0.f) atomicAdd(v + id.x, w.x * g);
-    if (w.y != 0.f) atomicAdd(v + id.y, w.y * g);
-    if (w.z != 0.f) atomicAdd(v + id.z, w.z * g);
-    if (w.w != 0.f) atomicAdd(v + id.w, w.w * g);
+    const int q0 = blockIdx.x * IDW_BWD_SPAN;
+    const int q1 = min(Q, q0 + IDW_BWD_SPAN);
+    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const float g = dout[static_cast<size_t>(b) * Q + q];
+        if (g == 0.f) continue;
+        const size_t o = (static_cast<size_t>(sb) * Q + q) * 4;
+        const int4 id = __ldg(reinterpret_cast<const int4*>(nbr_idx + o));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(nbr_w + o));
+        float* dst = priv ? acc : v;
+        if (w.x != 0.f) atomicAdd(dst + id.x, w.x * g);
+        if (w.y != 0.f) atomicAdd(dst + id.y, w.y * g);
+        if (w.z != 0.f) atomicAdd(dst + id.z, w.z * g);
+        if (w.w != 0.f) atomicAdd(dst + id.w, w.w * g);
+    }
+    if (priv) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            if (acc[i] != 0.f) atomicAdd(v + i, acc[i]);
+    }
 }
 
 static unsigned long long gcd_ull(unsigned long long a, unsigned long long b) {
@@ -430,7 +450,7 @@ extern "C" int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const floa
                                const int* src, float* dvals, int cap, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dout && nbr_idx && nbr_w && counts && dvals, "idw_knn_bwd: null pointer");
     const int Q = T * H * W;
-    dim3 grid(cdiv(Q, 256), B);
+    dim3 grid(cdiv(Q, IDW_BWD_SPAN), B);
     idw_interp_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, nbr_idx, nbr_w, counts, src, cap, dvals, Q);
     P2I_CHECK_LAUNCH("idw_interp_bwd_kernel");
     return P2I_OK;

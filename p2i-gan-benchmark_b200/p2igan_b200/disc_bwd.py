@@ -9,57 +9,109 @@ from ._lib import LIB, ptr, stream
 from .disc_ops import ALL_SN, TC_LAYERS, _state, conv_desc, conv_igemm, conv_wgrad, forward_ctx
 
 
-def _colsum(g, C):
-    out = torch.zeros(C, dtype=torch.float32, device=g.device)
+class _BwdBuffers:
+    """Persistent gradient buffers of one operand set + the device table of the spectral-norm backward."""
+
+    def __init__(self, mods, st, dev):
+        f32 = torch.float32
+        tc = {n: (Cout, Cin, KT, k, s2, (4 * Cin if s2 else cinp)) for n, Cout, Cin, KT, k, s2, cinp, _ in TC_LAYERS}
+        sizes = {}
+        for n in ALL_SN:
+            sizes[n] = st.w[n].numel() if n in tc else mods[n].weight_orig.numel()
+        nb = {n: mods[n].bias.numel() for n in ALL_SN}
+        total = sum(sizes.values()) + len(ALL_SN)
+        self.arena = torch.zeros(total, dtype=f32, device=dev)       # scratch, zeroed once per backward (single memset)
+        o = 0
+        self.G = {}
+        for n in ALL_SN:
+            self.G[n] = self.arena[o:o + sizes[n]]; o += sizes[n]
+        self.inner = self.arena[o:o + len(ALL_SN)]; o += len(ALL_SN)
+        self.mods, self.st, self.tc = mods, st, tc
+        self.key, self.table = None, None
+
+    def table_for(self, targets, dev):
+        """Device table of the spectral-norm backward writing (+=) into ``targets[name + '.weight_orig']``."""
+        key = tuple(targets[n + ".weight_orig"].data_ptr() for n in ALL_SN)
+        if key == self.key:
+            return self.table
+        mods, st, tc = self.mods, self.st, self.tc
+        tab = b""
+        for n in ALL_SN:
+            m = mods[n]
+            if n in tc:
+                Cout, Cin, KT, k, s2, cinp = tc[n]
+                packed = 1
+            else:
+                Cout, Cin = m.weight_orig.shape[0], m.weight_orig.shape[1]
+                per = m.weight_orig.numel() // (Cout * Cin)
+                KT, k, s2, cinp, packed = (3, 3, 0, Cin, 0) if per == 27 else ((1, 3, 0, Cin, 0) if per == 9 else (1, 1, 0, Cin, 0))
+            tab += struct.pack("<QQQQQQiiiiiiii", self.G[n].data_ptr(), m.weight_orig.data_ptr(), st.u[n].data_ptr(),
+                               st.v[n].data_ptr(), st.sig(n).data_ptr(), targets[n + ".weight_orig"].data_ptr(), Cout, Cin, KT,
+                               k, s2, cinp, packed, 0)
+        self.table = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(dev)
+        self.key = key
+        return self.table
+
+
+def prepare(D):
+    """Allocate the persistent backward buffers of every operand set (call once before CUDA-graph capture)."""
+    state = _state(D)
+    for st in state.sets:
+        if st.bwd is None:
+            st.bwd = _BwdBuffers(state.mods, st, state.dev)
+
+
+def _colsum(g, out):
+    C = g.shape[-1]
     LIB.call("p2i_colsum_bf16", ptr(g), ptr(out), g.numel() // C, C, stream())
-    return out
 
 
 def backward(D, ctx, dfused, need_params: bool, need_input: bool):
     """dfused f32 [B, (H/4)(W/4)] -> ({param name: grad}, dx f32 [B,T,1,H,W] or None)."""
-    st = _state(D)
+    state = _state(D)
+    st = ctx["set"]
+    mods = state.mods
     B, T, H, W, T2 = ctx["dims"]
     dev = dfused.device
     bf, f32 = torch.bfloat16, torch.float32
-    mods = st.mods
-    sig = ctx["sigma"]
-    w, wt = ctx["w"], ctx["wt"]
-
-    def sg(name):
-        i = ALL_SN.index(name)
-        return sig[i:i + 1]
-
-    grads = {}
-    G = {}                                   # dL/dW_sn per layer (packed or plain)
+    w, wt = st.w, st.wt
+    if st.bwd is None:
+        st.bwd = _BwdBuffers(mods, st, dev)
+    bb = st.bwd
+    bb.arena.zero_()
+    G = bb.G if need_params else {}
+    # gradient targets: preallocated .grad (flat-gradient mode, accumulated in place) or fresh zero buffers for autograd
+    tg, fresh = {}, {}
+    if need_params:
+        for n, p in D.named_parameters():
+            if n == "alpha3d" or not p.requires_grad:
+                continue
+            if p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == f32:
+                tg[n] = p.grad
+            else:
+                fresh[n] = torch.zeros_like(p, dtype=f32, memory_format=torch.contiguous_format)
+                tg[n] = fresh[n]
+    dbias = {n: tg[n + ".bias"] for n in ALL_SN} if need_params else {}
     dfused = dfused.detach().contiguous().float()
     h4, w4, h8, w8 = H // 4, W // 4, H // 8, W // 8
 
     # ---- tail
     d_o2d = torch.empty(B, h4, w4, dtype=f32, device=dev)
-    dalpha = torch.zeros((), dtype=f32, device=dev)
     dpre_z4 = torch.empty_like(ctx["z4"])
-    if need_params:
-        G["d3d.8"] = torch.zeros(128, dtype=f32, device=dev)
-        grads["d3d.8.bias"] = torch.zeros(1, dtype=f32, device=dev)
     LIB.call("p2i_disc_tail_bwd", ptr(dfused), ptr(ctx["o2d"]), ptr(D.alpha2d.detach()), ptr(ctx["z4"]),
-             ptr(mods["d3d.8"].weight_orig.detach()), ptr(sg("d3d.8")), ptr(d_o2d), ptr(dalpha), ptr(dpre_z4),
-             ptr(G.get("d3d.8")), ptr(grads.get("d3d.8.bias")), B, T2, h8, w8, 128, h4, w4, stream())
-    grads["alpha2d"] = dalpha
+             ptr(mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(d_o2d), ptr(tg.get("alpha2d")),
+             ptr(dpre_z4), ptr(G.get("d3d.8")), ptr(dbias.get("d3d.8")), B, T2, h8, w8, 128, h4, w4, stream())
 
     # ---- d2d.8
     dpre_y4 = torch.empty_like(ctx["y4"])
-    if need_params:
-        G["d2d.8"] = torch.zeros(256 * 9, dtype=f32, device=dev)
-        grads["d2d.8.bias"] = torch.zeros(1, dtype=f32, device=dev)
-    LIB.call("p2i_d2d_last_bwd", ptr(d_o2d), ptr(ctx["y4"]), ptr(mods["d2d.8"].weight_orig.detach()), ptr(sg("d2d.8")),
-             ptr(dpre_y4), ptr(G.get("d2d.8")), ptr(grads.get("d2d.8.bias")), B, h4, w4, 256, stream())
+    LIB.call("p2i_d2d_last_bwd", ptr(d_o2d), ptr(ctx["y4"]), ptr(mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")),
+             ptr(dpre_y4), ptr(G.get("d2d.8")), ptr(dbias.get("d2d.8")), B, h4, w4, 256, stream())
 
     def tc_layer(name, x_in, dpre, fdesc, ddesc, mask, out_shape):
-        """wgrad + bias grad (if needed) and dgrad of one tensor-core layer. Returns d(pre-activation) of the layer below."""
+        """wgrad + bias grad (if needed) and dgrad of one tensor-core layer -> d(pre-activation) of the layer below."""
         if need_params:
-            G[name] = torch.zeros(w[name].shape, dtype=f32, device=dev)
             conv_wgrad(x_in, dpre, G[name], fdesc)
-            grads[name + ".bias"] = _colsum(dpre, dpre.shape[-1])
+            _colsum(dpre, dbias[name])
         if ddesc is None:
             return None
         out = torch.empty(out_shape, dtype=bf, device=dev)
@@ -84,42 +136,21 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
     d = tc_layer("d3d.2", ctx["z1"], d, conv_desc(B, T, T, h4, w4, 128, 64, 3, 2, 1, 1),
                  conv_desc(B, T, T, h4, w4, 64, 128, 3, 2, 0, 1, mask_mode=2, out_mode=2), ctx["z1"], (B, T, H // 2, W // 2, 32))
     dx = torch.empty(B, T, H, W, dtype=f32, device=dev) if need_input else None
-    if need_params:
-        G["d3d.0"] = torch.zeros(32 * 27, dtype=f32, device=dev)
-        grads["d3d.0.bias"] = torch.zeros(32, dtype=f32, device=dev)
-    LIB.call("p2i_d3d_first_bwd", ptr(d), ptr(ctx["xf"]), ptr(mods["d3d.0"].weight_orig.detach()), ptr(sg("d3d.0")),
-             ptr(G.get("d3d.0")), ptr(grads.get("d3d.0.bias")), ptr(dx), B, T, H, W, stream())
+    LIB.call("p2i_d3d_first_bwd", ptr(d), ptr(ctx["xf"]), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")),
+             ptr(G.get("d3d.0")), ptr(dbias.get("d3d.0")), ptr(dx), B, T, H, W, stream())
     if need_input:
         LIB.call("p2i_disc_unpack_input_grad", ptr(d_a0), ptr(dx), B, 16, H, W, stream())
         dx = dx.view(B, T, 1, H, W)
 
-    # ---- spectral-norm backward (+ un-pack of tensor-core gradients), one launch for all 10 layers
+    # ---- spectral-norm backward (+ un-pack of tensor-core gradients): two launches for all 10 layers
     if need_params:
-        tc = {n: (Cout, Cin, KT, k, s2, cinp if not s2 else 4 * Cin) for n, Cout, Cin, KT, k, s2, cinp, _ in TC_LAYERS}
-        tab = b""
-        outs = {}
-        for n in ALL_SN:
-            m = mods[n]
-            dW = torch.empty_like(m.weight_orig)
-            outs[n] = dW
-            if n in tc:
-                Cout, Cin, KT, k, s2, cinp = tc[n]
-                packed = 1
-            else:
-                Cout, Cin = m.weight_orig.shape[0], m.weight_orig.shape[1]
-                per = m.weight_orig.numel() // (Cout * Cin)
-                KT, k, s2, cinp, packed = (3, 3, 0, Cin, 0) if per == 27 else ((1, 3, 0, Cin, 0) if per == 9 else (1, 1, 0, Cin, 0))
-            tab += struct.pack("<QQQQQQiiiiiiii", G[n].data_ptr(), m.weight_orig.data_ptr(), ctx["u"][n].data_ptr(),
-                               ctx["v"][n].data_ptr(), sg(n).data_ptr(), dW.data_ptr(), Cout, Cin, KT, k, s2, cinp, packed, 0)
-        tab_dev = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(dev)
-        LIB.call("p2i_spectral_norm_bwd", ptr(tab_dev), len(ALL_SN), stream())
-        for n in ALL_SN:
-            grads[n + ".weight_orig"] = outs[n]
-    return grads, dx
+        LIB.call("p2i_spectral_norm_bwd", ptr(bb.table_for(tg, dev)), len(ALL_SN), ptr(bb.inner), stream())
+    return fresh, dx
 
 
 class DiscriminatorFn(torch.autograd.Function):
-    """Whole-discriminator autograd node."""
+    """Whole-discriminator autograd node.  Parameters with a preallocated .grad are accumulated in place by the kernels
+    (flat-gradient mode); the others receive their gradient through autograd as usual."""
 
     @staticmethod
     def forward(ctx, D, x, *params):
@@ -131,7 +162,7 @@ class DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         need_input = ctx.needs_input_grad[1]
-        need_params = any(ctx.needs_input_grad[2:])
+        need_params = any(f for f, n in zip(ctx.needs_input_grad[2:], ctx.names) if n != "alpha3d")
         grads, dx = backward(ctx.D, ctx.saved, dout, need_params, need_input)
         ctx.saved = None
         pg = tuple(grads.get(n) if (need_params and ctx.needs_input_grad[2 + i]) else None for i, n in enumerate(ctx.names))

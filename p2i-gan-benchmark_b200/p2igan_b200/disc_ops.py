@@ -59,23 +59,23 @@ def _mod(D, name):
     return getattr(D, seq)[int(idx)]
 
 
-class DiscState:
-    """Per-module cache: device tables, packed bf16 operands and sigma scalars."""
+N_SETS = 3   # D is called three times per training step (fake, real, fake-for-G): each call owns one operand set
 
-    def __init__(self, D):
-        dev = D.alpha2d.device
-        self.dev = dev
+
+class _OperandSet:
+    """Packed bf16 operands, sigma scalars and the (u, v) snapshot of ONE forward call."""
+
+    def __init__(self, mods, dev):
         self.sigma = torch.zeros(len(ALL_SN), dtype=torch.float32, device=dev)
-        mods = {n: _mod(D, n) for n in ALL_SN}
-        self.mods = mods
-        self.key = tuple(m.weight_orig.data_ptr() for m in mods.values())
+        self.u = {n: torch.empty_like(mods[n].weight_u) for n in ALL_SN}
+        self.v = {n: torch.empty_like(mods[n].weight_v) for n in ALL_SN}
         sn = b""
         for i, n in enumerate(ALL_SN):
             m = mods[n]
             rows = m.weight_orig.shape[0]
             cols = m.weight_orig.numel() // rows
-            sn += struct.pack("<QQQQii", m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
-                              self.sigma[i:i + 1].data_ptr(), rows, cols)
+            sn += struct.pack("<QQQQQQii", m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
+                              self.sigma[i:i + 1].data_ptr(), self.u[n].data_ptr(), self.v[n].data_ptr(), rows, cols)
         self.sn_table = torch.frombuffer(bytearray(sn), dtype=torch.uint8).to(dev)
         self.w: Dict[str, torch.Tensor] = {}
         self.wt: Dict[str, torch.Tensor] = {}
@@ -89,10 +89,28 @@ class DiscState:
             pk += struct.pack("<QQQQiiiiiiii", mods[name].weight_orig.data_ptr(), self.sigma[si:si + 1].data_ptr(),
                               self.w[name].data_ptr(), self.wt[name].data_ptr(), Cout, Cin, KT, k, s2, cinp, keep_t, 0)
         self.pack_table = torch.frombuffer(bytearray(pk), dtype=torch.uint8).to(dev)
+        self.bwd = None          # lazily built by disc_bwd (persistent gradient buffers + device table)
 
     def sig(self, name):
         i = ALL_SN.index(name)
         return self.sigma[i:i + 1]
+
+
+class DiscState:
+    """Per-module cache: N_SETS rotating operand sets (so a saved forward context stays valid until its backward ran,
+    without cloning anything) and their device tables."""
+
+    def __init__(self, D):
+        self.dev = D.alpha2d.device
+        self.mods = {n: _mod(D, n) for n in ALL_SN}
+        self.key = tuple(m.weight_orig.data_ptr() for m in self.mods.values())
+        self.sets = [_OperandSet(self.mods, self.dev) for _ in range(N_SETS)]
+        self.calls = 0
+
+    def next_set(self) -> _OperandSet:
+        s = self.sets[self.calls % N_SETS]
+        self.calls += 1
+        return s
 
 
 def _state(D) -> DiscState:
@@ -113,13 +131,15 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
         raise ValueError(f"P2IDiscriminator expects {D.in_channels} frames, got {T * C}")
     if H % 16 or W % 16:
         raise ValueError("P2IDiscriminator requires H and W to be multiples of 16")
-    st = _state(D)
+    state = _state(D)
+    st = state.next_set()
+    mods = state.mods
     dev = x.device
     xf = x.detach().reshape(B, T, H, W).contiguous().float()
     LIB.call("p2i_spectral_norm", ptr(st.sn_table), len(ALL_SN), 1 if D.training else 0, stream())
     LIB.call("p2i_disc_pack_weights", ptr(st.pack_table), len(TC_LAYERS), stream())
     bf = torch.bfloat16
-    bias = {n: st.mods[n].bias.detach() for n in ALL_SN}
+    bias = {n: mods[n].bias.detach() for n in ALL_SN}
     # ---- 2-D branch
     a0 = torch.empty(B, H, W, 64, dtype=bf, device=dev)
     LIB.call("p2i_disc_pack_input", ptr(xf), ptr(a0), B, 16, H, W, stream())
@@ -132,11 +152,11 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     y4 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
     conv_igemm(y3, st.w["d2d.6"], conv_desc(B, 1, 1, H // 4, W // 4, 256, 256, 1, 3, 1, 0, act=2), bias=bias["d2d.6"], out=y4)
     o2d = torch.empty(B, H // 4, W // 4, dtype=torch.float32, device=dev)
-    LIB.call("p2i_d2d_last_fwd", ptr(y4), ptr(st.mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")), ptr(bias["d2d.8"]),
+    LIB.call("p2i_d2d_last_fwd", ptr(y4), ptr(mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")), ptr(bias["d2d.8"]),
              ptr(o2d), B, H // 4, W // 4, 256, stream())
     # ---- 3-D branch
     z1 = torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev)
-    LIB.call("p2i_d3d_first_fwd", ptr(xf), ptr(st.mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")), ptr(bias["d3d.0"]),
+    LIB.call("p2i_d3d_first_fwd", ptr(xf), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")), ptr(bias["d3d.0"]),
              ptr(z1), B, T, H, W, stream())
     z2 = torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev)
     conv_igemm(z1, st.w["d3d.2"], conv_desc(B, T, T, H // 4, W // 4, 128, 64, 3, 2, 1, 1, act=2, out_mode=1), bias=bias["d3d.2"], out=z2)
@@ -148,14 +168,12 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     # ---- tail
     m = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev)
     fused = torch.empty(B, (H // 4) * (W // 4), dtype=torch.float32, device=dev)
-    LIB.call("p2i_disc_tail_fwd", ptr(z4), ptr(st.mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(bias["d3d.8"]),
+    LIB.call("p2i_disc_tail_fwd", ptr(z4), ptr(mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(bias["d3d.8"]),
              ptr(o2d), ptr(D.alpha2d.detach()), ptr(m), ptr(fused), B, T2, H // 8, W // 8, 128, H // 4, W // 4, stream())
     ctx = None
     if save:
         ctx = dict(xf=xf, a0=a0, y1=y1, y2=y2, y3=y3, y4=y4, o2d=o2d, z1=z1, z2=z2, z3=z3, z4=z4, m=m, dims=(B, T, H, W, T2),
-                   sigma=st.sigma.clone(), w={k: v.clone() for k, v in st.w.items()}, wt={k: v.clone() for k, v in st.wt.items()},
-                   u={n: st.mods[n].weight_u.detach().clone() for n in ALL_SN},
-                   v={n: st.mods[n].weight_v.detach().clone() for n in ALL_SN})
+                   set=st)
     return fused, ctx
 
 

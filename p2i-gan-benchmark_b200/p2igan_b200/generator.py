@@ -79,7 +79,7 @@ class P2IGenerator(BaseNetwork):
             wc = {"ptr_key": ptr_key, "ver_key": None, "bufs": bufs, "bufs_t": bufs_t,
                   "table": torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(dev)}
             self._wcache = wc
-        if wc["ver_key"] != ver_key:
+        if wc["ver_key"] != ver_key or self.training:      # training: weights change every step (also under CUDA graphs)
             ops.doconv_compose(wc["table"], len(convs), max(c.in_channels for _, c in convs))
             s = self.Convsin[0].main[0]
             wc["stem"] = ops.doconv_compose_stem(s.W.detach(), s.D.detach(), s.D_diag.detach())
@@ -186,16 +186,30 @@ class P2IGenerator(BaseNetwork):
         sv["r"], sv["w_out"], sv["out"] = r, w_out, out
         return out, sv
 
+    def _grad_targets(self):
+        """{name: tensor to accumulate the gradient into}.  Parameters whose .grad is preallocated (flat-gradient
+        mode of the trainer) are accumulated in place; the others get a fresh zero buffer that is handed to autograd."""
+        tg, fresh = {}, {}
+        for n, p in self.named_parameters():
+            if not p.requires_grad:
+                continue
+            if p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32:
+                tg[n] = p.grad
+            else:
+                fresh[n] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                tg[n] = fresh[n]
+        return tg, fresh
+
     def _backward_train(self, sv, dout):
-        """dout f32 [B,16,H,W] -> {parameter name: gradient}."""
+        """dout f32 [B,16,H,W] -> {parameter name: gradient tensor for autograd} (empty in flat-gradient mode)."""
         wc = sv["wc"]
         bufs_t = wc["bufs_t"]
         gt = self._grad_table(wc)
         gt["arena"].zero_()
         gviews = gt["views"]
-        grads: Dict[str, torch.Tensor] = {}
+        tg, fresh = self._grad_targets()
         d, dw_out = ops.head_bwd(dout.contiguous(), sv["out"], sv["r"], sv["w_out"])
-        grads["ConvsOut.0.main.0.W"] = dw_out.reshape(16, 16, 1)
+        tg["ConvsOut.0.main.0.W"].add_(dw_out.reshape(16, 16, 1))
 
         def eblock_bwd(level, d):
             base = level * 2 * self.num_res
@@ -209,11 +223,9 @@ class P2IGenerator(BaseNetwork):
 
         def up_bwd(i, d):
             x, z, pos, bias = sv["up"][i]
-            dz, dbias, dpos = ops.upmod_bwd(z, pos, bias, d)
-            dwp = ops.conv2d_wgrad(x, dz, 1)
-            grads[f"UP.{i}.pos"] = dpos.reshape(1, 1, *dpos.shape)
-            grads[f"UP.{i}.proj.bias"] = dbias
-            grads[f"UP.{i}.proj.weight"] = dwp.reshape(dwp.shape[1], dwp.shape[2], 1, 1)
+            dz = ops.upmod_bwd(z, pos, bias, d, tg[f"UP.{i}.proj.bias"], tg[f"UP.{i}.pos"])
+            wv = tg[f"UP.{i}.proj.weight"]
+            ops.conv2d_wgrad(x, dz, 1, out=wv.view(1, wv.shape[0], wv.shape[1]))
             return ops.conv2d_cl(dz, wc["up_t"][i])
 
         d = eblock_bwd(0, d)
@@ -227,30 +239,25 @@ class P2IGenerator(BaseNetwork):
         d_stem = ops.pyramid_bwd(sv["stem"], d_x4, d_x8)
         dx_in, dw_stem = ops.stem_bwd(d_stem, sv["x_in"], wc["stem"])
         s = self.Convsin[0].main[0]
-        dWs, dDs = ops.doconv_compose_stem_bwd(s.W.detach(), s.D.detach(), s.D_diag.detach(), dw_stem)
-        grads["Convsin.0.main.0.W"], grads["Convsin.0.main.0.D"] = dWs, dDs
+        ops.doconv_compose_stem_bwd(s.W.detach(), s.D.detach(), s.D_diag.detach(), dw_stem, tg["Convsin.0.main.0.W"],
+                                    tg["Convsin.0.main.0.D"])
         # InputBlock
         inp, pts, counts, src, table = sv["ictx"]
         dvals = ops.idw_knn_bwd(dx_in, table, counts, src, pts.shape[1])
         w0, b0, w1, b1 = (p.detach().contiguous() for p in self.input.gate_params())
-        dw0, db0, dw1, db1 = ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals)
-        grads["input.layers.0.conv.weight"], grads["input.layers.0.conv.bias"] = dw0, db0
-        grads["input.layers.1.conv.weight"], grads["input.layers.1.conv.bias"] = dw1, db1
-        # DO-Conv composition backward for the 32 ResBlock convs (one batched launch pair)
+        ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals, tg["input.layers.0.conv.weight"],
+                            tg["input.layers.0.conv.bias"], tg["input.layers.1.conv.weight"], tg["input.layers.1.conv.bias"])
+        # DO-Conv composition backward for the 32 ResBlock convs (one batched launch pair); the device table is cached
         convs = list(self._res_convs())
-        names = []
-        for level in range(4):
-            for r in range(self.num_res):
-                for j in range(2):
-                    names.append(f"Decoder.{level}.layers.{r}.main.{j}.main.0")
-        outs = [(torch.empty_like(c.W), torch.empty_like(c.D)) for _, c in convs]
-        tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), dW.data_ptr(),
-                                   dD.data_ptr(), c.in_channels) for (_, c), g, (dW, dD) in zip(convs, gviews, outs)])
-        tab_dev = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
-        ops.doconv_compose_bwd(tab_dev, len(convs), max(c.in_channels for _, c in convs))
-        for n, (dW, dD) in zip(names, outs):
-            grads[n + ".W"], grads[n + ".D"] = dW, dD
-        return grads
+        names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
+        key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
+        if gt.get("bwd_key") != key:
+            tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), tg[n + ".W"].data_ptr(),
+                                       tg[n + ".D"].data_ptr(), c.in_channels) for (_, c), g, n in zip(convs, gviews, names)])
+            gt["bwd_table"] = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
+            gt["bwd_key"] = key
+        ops.doconv_compose_bwd(gt["bwd_table"], len(convs), max(c.in_channels for _, c in convs))
+        return fresh
 
 
 class _GeneratorFn(torch.autograd.Function):

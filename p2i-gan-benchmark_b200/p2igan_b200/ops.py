@@ -45,13 +45,12 @@ def gate_points_fwd(masked: Tensor, pts: Tensor, counts: Tensor, w0, b0, w1, b1,
     return vals, l1
 
 
-def gate_points_bwd(masked, pts, counts, w0, b0, w1, b1, dvals):
+def gate_points_bwd(masked, pts, counts, w0, b0, w1, b1, dvals, dw0, db0, dw1, db1):
+    """Accumulates (atomics) into dw0 [16,16,1], db0 [16], dw1, db1 (float32, contiguous)."""
     B, T, H, W = masked.shape
     cap = pts.shape[1]
-    dw0, db0, dw1, db1 = (torch.zeros_like(t, dtype=torch.float32) for t in (w0, b0, w1, b1))
     LIB.call("p2i_gate_points_bwd", ptr(masked), ptr(pts), ptr(counts), cap, ptr(w0), ptr(b0), ptr(w1), ptr(b1),
              ptr(_chk(dvals, torch.float32, "dvals")), ptr(dw0), ptr(db0), ptr(dw1), ptr(db1), B, T, H, W, stream())
-    return dw0, db0, dw1, db1
 
 
 def idw_knn_fwd(pts, vals, counts, src, shape: Tuple[int, int, int], tau: float, table=None):
@@ -180,16 +179,15 @@ def head_bwd(dout: Tensor, out: Tensor, x: Tensor, w: Tensor):
     return dx, dw
 
 
-def upmod_bwd(z: Tensor, pos: Tensor, bias: Tensor, dout: Tensor):
-    """-> (dz [B,h,w,C] bf16, dbias f32 [C], dpos f32 [2h,2w])."""
+def upmod_bwd(z: Tensor, pos: Tensor, bias: Tensor, dout: Tensor, dbias: Tensor, dpos: Tensor):
+    """-> dz [B,h,w,C] bf16; accumulates into dbias f32 [C] and dpos f32 [...,2h,2w]."""
     B, h, w, C = z.shape
     scratch = torch.empty_like(dout)
     dz = torch.empty_like(z)
-    dbias = torch.zeros(C, dtype=torch.float32, device=z.device)
-    dpos = torch.zeros(2 * h, 2 * w, dtype=torch.float32, device=z.device)
     LIB.call("p2i_upmod_bwd", ptr(z), ptr(_chk(pos, torch.float32, "pos")), ptr(_chk(bias, torch.float32, "bias")),
-             ptr(_chk(dout, torch.bfloat16, "dout")), ptr(scratch), ptr(dz), ptr(dbias), ptr(dpos), B, h, w, C, stream())
-    return dz, dbias, dpos
+             ptr(_chk(dout, torch.bfloat16, "dout")), ptr(scratch), ptr(dz), ptr(_chk(dbias, torch.float32, "dbias")),
+             ptr(_chk(dpos, torch.float32, "dpos")), B, h, w, C, stream())
+    return dz
 
 
 def pyramid_bwd(stem: Tensor, dx4: Tensor, dx8: Tensor) -> Tensor:
@@ -212,9 +210,7 @@ def doconv_compose_bwd(table_dev: Tensor, n_layers: int, max_channels: int) -> N
     LIB.call("p2i_doconv_compose_bwd", ptr(table_dev), n_layers, max_channels, stream())
 
 
-def doconv_compose_stem_bwd(W, D, D_diag, dDoW):
-    dW = torch.empty_like(W)
-    dD = torch.empty_like(D)
+def doconv_compose_stem_bwd(W, D, D_diag, dDoW, dW, dD):
+    """Accumulates into dW [64,4,9] and dD [16,9,9]."""
     LIB.call("p2i_doconv_compose_stem_bwd", ptr(W), ptr(D), ptr(D_diag), ptr(_chk(dDoW, torch.float32, "dDoW")), ptr(dW),
              ptr(dD), stream())
-    return dW, dD

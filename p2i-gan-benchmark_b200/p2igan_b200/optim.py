@@ -1,6 +1,7 @@
 """Fused multi-tensor Adam on sm_100a with torch.optim.Adam's state layout (``step``, ``exp_avg``, ``exp_avg_sq``),
 so checkpoints written by the reference trainer (scripts/train.py:475-485, ``optimizer_g`` / ``optimizer_d``) load
-unchanged.  One kernel launch per optimiser step."""
+unchanged.  One kernel launch per optimiser step; the step counter lives on the device (as torch's
+``capturable=True`` Adam does), which makes the whole update CUDA-graph capturable."""
 from __future__ import annotations
 
 import struct
@@ -14,6 +15,21 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
+
+    def _init_state(self, group):
+        plist = [p for p in group["params"] if p.requires_grad or p.grad is not None]
+        dev = plist[0].device
+        step = None
+        for p in plist:
+            st = self.state[p]
+            if "exp_avg" not in st:
+                if step is None:
+                    step = torch.zeros((), dtype=torch.float32, device=dev)
+                st["step"] = step                     # one shared device counter per group
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            elif not st["step"].is_cuda:              # state loaded from a torch.optim.Adam checkpoint
+                st["step"] = st["step"].to(dev, torch.float32)
 
     def _table(self, gi, plist):
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
@@ -40,19 +56,13 @@ class FusedAdam(torch.optim.Optimizer):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
                 continue
+            self._init_state(group)
             for p in plist:
-                st = self.state[p]
-                if not st:
-                    st["step"] = torch.tensor(0.0)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
                     raise RuntimeError("FusedAdam needs contiguous float32 parameters and gradients")
-                st["step"] += 1
-            step = int(self.state[plist[0]]["step"])
             _, tens, chunks, n = self._table(gi, plist)
-            LIB.call("p2i_adam_step", ptr(tens), ptr(chunks), n, float(group["lr"]), float(group["betas"][0]),
-                     float(group["betas"][1]), float(group["eps"]), step, float(grad_scale), stream())
+            LIB.call("p2i_adam_step", ptr(tens), ptr(chunks), n, ptr(self.state[plist[0]]["step"]), float(group["lr"]),
+                     float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(grad_scale), stream())
             # the kernel wrote the parameters behind autograd's back: bump their version counters so that
             # version-keyed caches (composed DO-Conv operands) see the update
             torch.autograd.graph.increment_version(plist)

@@ -5,19 +5,49 @@
                  freeze D -> adv = gan_loss(D(preds), real, is_disc=False) * adversarial_weight -> loss_g += adv
     G backward / Adam;  unfreeze D
 
-Data parallel (new relative to the reference, SURVEY.md 8e): one process per GPU, each rank holds its own events;
-gradients are summed with ONE flat NCCL all-reduce per model and the 1/world_size factor is folded into the fused
-Adam kernel.  Loss scalars stay on the device (no host synchronisation inside the step).
+Gradients live in ONE flat fp32 buffer per model (``p.grad`` are views): the backward kernels accumulate into it
+directly, ``zero_grad`` is a single memset, the data-parallel exchange is a single NCCL all-reduce(sum) over NVLink
+per model (1/world_size folded into the fused Adam kernel), and the Adam work table never changes.  Nothing in the
+step synchronises with the host, so the whole iteration can be captured in a CUDA graph (``GraphedStep``).
+
+Data parallelism is new relative to the reference: one process per GPU, each rank holds its own
+events; N ranks x b events  ==  one rank x N*b events up to fp32 summation order.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Optional
+from typing import Any, Dict, Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
 
 from .losses import ReconstructionLoss, gan_loss
 from .optim import FusedAdam
+
+
+class FlatGrads:
+    """Flat fp32 gradient buffer; ``p.grad`` of every given parameter becomes a view into it."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group=None) -> float:
+        """Sum over data-parallel ranks (one collective); returns the factor that turns the sum into a mean."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        world = dist.get_world_size(group)
+        if world == 1:
+            return 1.0
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
 
 
 class GANTrainStep:
@@ -33,28 +63,23 @@ class GANTrainStep:
         self.rec = ReconstructionLoss(k1_alpha=loss_cfg.get("k1_weight", 0.0))
         oc = cfg["train"]["optimizer"]
         betas = (oc.get("beta1", 0.0), oc.get("beta2", 0.99))
-        self.opt_g = FusedAdam([p for p in generator.parameters()], lr=oc["lr"], betas=betas)
-        self.opt_d = FusedAdam([p for p in discriminator.parameters()], lr=oc["lr"], betas=betas) if discriminator is not None else None
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-
-    # ---- data-parallel gradient exchange: one flat all-reduce(sum) per model
-    def _allreduce(self, params):
-        if self.world == 1:
-            return 1.0
-        grads = [p.grad for p in params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
-        return 1.0 / self.world
+        self.flat_g = FlatGrads(generator.parameters())
+        self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
+        self.flat_d = self.opt_d = None
+        if self.use_gan:
+            # alpha3d never receives a gradient in the reference (unused Parameter, models/p2igan.py:145): keep grad None
+            self.flat_d = FlatGrads(p for n, p in discriminator.named_parameters() if n != "alpha3d")
+            self.opt_d = FusedAdam(self.flat_d.params, lr=oc["lr"], betas=betas)
+            from . import disc_bwd
+            disc_bwd.prepare(discriminator)
 
     def _gan(self, logits, real, is_disc):
         return gan_loss(logits, real, loss_type=self.gan_type, is_disc=is_disc, target_real_label=self.real_label,
                         target_fake_label=self.fake_label)
 
     def step(self, frames, masked_frames, masks) -> Dict[str, torch.Tensor]:
-        """Returns device scalars {rec, pool, reg, adv, dis, total}; call .item() outside the hot loop."""
+        """Returns device scalars {rec, pool, reg, adv, dis, total}; read them outside the hot loop."""
         G, D = self.G, self.D
         preds = G(masked_frames, masks)
         loss_g, pool, reg = self.rec.tensors(preds, frames)
@@ -65,19 +90,47 @@ class GANTrainStep:
             logits_fake = D(preds.detach())
             logits_real = D(frames)
             loss_d = (self._gan(logits_real, True, True) + self._gan(logits_fake, False, True)) * 0.5
-            self.opt_d.zero_grad(set_to_none=True)
+            self.flat_d.zero()
             loss_d.backward()
-            self.opt_d.step(grad_scale=self._allreduce(list(D.parameters())))
+            self.opt_d.step(grad_scale=self.flat_d.all_reduce(self.pg))
             for p in D.parameters():
                 p.requires_grad_(False)
             adv = self._gan(D(preds), True, False) * self.adv_w
             loss_g = loss_g + adv
             out["adv"], out["dis"] = adv.detach(), loss_d.detach()
-        self.opt_g.zero_grad(set_to_none=True)
+        self.flat_g.zero()
         loss_g.backward()
-        self.opt_g.step(grad_scale=self._allreduce(list(G.parameters())))
+        self.opt_g.step(grad_scale=self.flat_g.all_reduce(self.pg))
         if self.use_gan:
             for p in D.parameters():
                 p.requires_grad_(True)
         out["total"] = loss_g.detach()
         return out
+
+
+class GraphedStep:
+    """CUDA-graph replay of a host-sync-free callable with fixed input shapes (training step or inference forward):
+    ``warmup`` eager calls on a side stream, one capture, then every call = copy inputs into the static buffers +
+    one graph launch (no per-kernel CPU launch cost)."""
+
+    def __init__(self, fn, example_inputs, warmup: int = 3):
+        self.static_in = [torch.empty_like(t) for t in example_inputs]
+        for s, t in zip(self.static_in, example_inputs):
+            s.copy_(t)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for s, t in zip(self.static_in, inputs):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

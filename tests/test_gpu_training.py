@@ -91,7 +91,7 @@ def test_doconv_compose_fwd_bwd():
     ref_t = dow.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, C, C)
     assert rel_l2(out_t.float(), ref_t) < 4e-3
     gd = gdow.to(DEV).contiguous()
-    dW, dD = torch.empty_like(Wc), torch.empty_like(Dc)
+    dW, dD = torch.zeros_like(Wc), torch.zeros_like(Dc)          # the backward accumulates (+=)
     tabg = torch.frombuffer(bytearray(pack_do_grad_table([(Wc.data_ptr(), Dc.data_ptr(), Ddc.data_ptr(), gd.data_ptr(),
                                                            dW.data_ptr(), dD.data_ptr(), C)])), dtype=torch.uint8).to(DEV)
     ops.doconv_compose_bwd(tabg, 1, C)
@@ -110,7 +110,9 @@ def test_losses_fwd_bwd(golden):
     loss, d = ReconstructionLoss(0.05)(pc, frames.to(DEV), None)
     (loss * 1.0).backward()
     gl = golden["loss32"]
-    assert abs(float(loss) - gl["total"]) < 1e-5 and abs(d["pool"] - gl["pool"]) < 1e-5 and abs(d["reg"] - gl["reg"]) < 1e-5
+    # fp32 reductions with atomically ordered partial sums: a few ulp
+    assert abs(float(loss.detach()) - gl["total"]) < 1e-5 * abs(gl["total"]) + 1e-6
+    assert abs(d["pool"] - gl["pool"]) < 1e-5 * abs(gl["pool"]) + 1e-6 and abs(d["reg"] - gl["reg"]) < 1e-5 * abs(gl["reg"]) + 1e-6
     assert rel_l2(pc.grad, pr.grad) < 1e-4
     lt = golden["d32"]["logits_train"]
     for kw, key in [(dict(target_is_real=True, loss_type="hinge", is_disc=True), "hinge_d_real"),
