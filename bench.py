@@ -292,7 +292,8 @@ def run_ours(args):
             return G(mf, mk)
 
     # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch
-    graphed = None if args.no_graph else GraphedStep(eager, batches[0], warmup=3)
+    # (multi-GPU runs launch eagerly: the NCCL all-reduces sit between kernels of the step and are not captured)
+    graphed = None if (args.no_graph or (world > 1 and train)) else GraphedStep(eager, batches[0], warmup=3)
     run = graphed if graphed is not None else eager
 
     def step(i):
