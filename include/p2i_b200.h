@@ -284,6 +284,19 @@ int p2i_gan_loss_bwd(const float* logits, long long n, int mode, float label, co
                      float* dlogits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Metrics  (p2igan_bench/metrics/metric.py:16-183)
+ * ------------------------------------------------------------------------------------------- */
+
+/* One RainfallMetricSuite.update(): pred/target f32 [N,H,W] (N = B*T frames).  thresholds (host, <= 4) are rain-rate
+ * thresholds applied to R = 0.036*10^(x/16); scales (host, <= 4, each in {1,2,4,8}) are FSS box sizes.
+ * scratch: double [50], zero-filled once by the caller (left clean after every call).
+ * state: float32 [51] streaming state, layout: [0] abs_sum [1] squared_sum [2] n_obs | [3+4t+k] hits, misses, false
+ * alarms, correct negatives of threshold t | [19+4t+s] FSS score_sum | [35+4t+s] FSS counts (per update call, as in
+ * metric.py:168-169).  apply_transform selects whether MAE/RMSE use the transformed values (metric.py:46-48). */
+int p2i_metrics_update(const float* pred, const float* target, int N, int H, int W, const float* thresholds, int n_thr,
+                       const int* scales, int n_scale, int apply_transform, double* scratch, float* state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimiser  (torch.optim.Adam as used by scripts/train.py:125-136)
  * ------------------------------------------------------------------------------------------- */
 typedef struct P2iAdamTensor {
@@ -299,6 +312,11 @@ typedef struct P2iAdamTensor {
 int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 int p2i_adam_chunk_elems(void);
+
+/* Sliding-window blend of scripts/infer.py:237-245: preds f32 [n_win, stride, HW] (window w starts at frame w*step) ->
+ * out f32 [L, HW] = clip(scale * mean over covering windows, 0). */
+int p2i_window_blend(const float* preds, float* out, int L, int HW, int stride, int step, int n_win, float scale,
+                     void* stream);
 
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);

@@ -267,3 +267,37 @@ extern "C" int p2i_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, 
     P2I_CHECK_LAUNCH("nhwc_to_nchw_kernel");
     return P2I_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Sliding-window blend of scripts/infer.py:237-245: frame l of an event of L frames is the mean of the predictions of
+// every window [s, s+stride) that covers it (windows start every `step` frames; tail windows were padded by repeating
+// the last frame and contribute only their valid part), scaled by output_scale and clipped at 0.
+// preds f32 [n_win, stride, HW] -> out f32 [L, HW]
+// ------------------------------------------------------------------------------------------------
+namespace p2i {
+__global__ void __launch_bounds__(256) window_blend_kernel(const float* __restrict__ preds, float* __restrict__ out, int L, int HW,
+                                                           int stride, int step, int n_win, float scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(L) * HW) return;
+    const int l = static_cast<int>(i / HW), pix = static_cast<int>(i - static_cast<long long>(l) * HW);
+    float acc = 0.f, cnt = 0.f;
+    for (int w = 0; w < n_win; ++w) {
+        const int s = w * step;
+        if (l >= s && l < s + stride) {
+            acc += preds[(static_cast<size_t>(w) * stride + (l - s)) * HW + pix];
+            cnt += 1.f;
+        }
+    }
+    out[i] = fmaxf(acc / fmaxf(cnt, 1e-5f) * scale, 0.f);
+}
+}  // namespace p2i
+
+extern "C" int p2i_window_blend(const float* preds, float* out, int L, int HW, int stride, int step, int n_win, float scale,
+                                void* stream) {
+    P2I_CHECK_ARG(preds && out && L > 0 && HW > 0 && stride > 0 && step > 0 && n_win > 0, "window_blend: bad arguments");
+    const long long n = static_cast<long long>(L) * HW;
+    p2i::window_blend_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, p2i::as_stream(stream)>>>(preds, out, L, HW, stride, step,
+                                                                                                        n_win, scale);
+    P2I_CHECK_LAUNCH("window_blend_kernel");
+    return P2I_OK;
+}

@@ -2,11 +2,21 @@
 
 Public surface mirrors what the reference's scripts import:
 ``build_generator``, ``build_discriminator``, ``P2IGenerator``, ``P2IDiscriminator``,
-``ReconstructionLoss``, ``gan_loss``, ``MetricConfig``, ``RainfallMetricSuite``.
+``ReconstructionLoss``, ``gan_loss``, ``MetricConfig``, ``RainfallMetricSuite``; plus the pieces the reference does
+not have: ``FusedAdam``, ``GANTrainStep`` (one iteration in scripts/train.py's order, data parallel, CUDA-graph
+capturable) and ``sliding_window_infer`` (scripts/infer.py's window loop, batched).
 Every op is a hand-written CUDA kernel in ``libp2i_sm100a.so`` (C ABI: include/p2i_b200.h);
 there is no CPU, PyTorch-eager or Triton fallback.
 """
+from .discriminator import P2IDiscriminator  # noqa: F401
 from .generator import P2IGenerator  # noqa: F401
+from .infer import sliding_window_infer  # noqa: F401
+from .losses import ReconstructionLoss, gan_loss  # noqa: F401
+from .metrics import MetricConfig, RainfallMetricSuite, transform  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .registry import build_discriminator, build_generator  # noqa: F401
+from .train_step import FlatGrads, GANTrainStep, GraphedStep  # noqa: F401
 
-__all__ = ["P2IGenerator", "build_generator", "build_discriminator"]
+__all__ = ["P2IGenerator", "P2IDiscriminator", "build_generator", "build_discriminator", "ReconstructionLoss", "gan_loss",
+           "MetricConfig", "RainfallMetricSuite", "transform", "FusedAdam", "GANTrainStep", "GraphedStep", "FlatGrads",
+           "sliding_window_infer"]

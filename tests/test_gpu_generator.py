@@ -193,3 +193,25 @@ def test_generator_batch_full_size_properties():
     assert torch.equal(a, b)
     assert torch.equal(a[2:3], c)
     assert bool(torch.isfinite(a).all()) and float(a.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("L", [16, 23, 5])
+def test_sliding_window_inference_matches_oracle(L):
+    """scripts/infer.py's window loop (stride 16, overlap 12, tail padding, overlap mean, x255, clip) -- batched."""
+    from p2igan_b200 import sliding_window_infer
+    G, sd = _generator_pair(32, 32, 2024, True)
+    frames, masked, masks = synth.make_batch(1, L, 32, 32, 12, 4)
+    ref = O.sliding_window_infer(sd, masked, masks)
+    out = sliding_window_infer(G, masked.to(DEV), masks.to(DEV))
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape == (L, 1, 32, 32)
+    d = (out.cpu() - ref).abs() / 255.0
+    assert float(d.max()) < 5e-2 and float(d.mean()) < 5e-3
+    assert float(out.min()) >= 0.0
+
+
+def test_drop_in_import_paths():
+    import p2igan_bench.metrics as m
+    import p2igan_bench.models as mo
+    import p2igan_bench.modules as md
+    assert mo.build_generator is not None and md.ReconstructionLoss is not None and m.RainfallMetricSuite is not None

@@ -1,0 +1,69 @@
+"""GPU parity: fused metric kernel vs the CPU oracle suite (itself pinned to the reference golden). Gate: abs 1e-3
+(north star), observed ~1e-6."""
+import math
+
+import pytest
+import torch
+
+import synth
+from oracle import p2i_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _compare(ours, ref, tol=1e-3):
+    assert set(ours) - {"ssim"} == set(ref)
+    assert math.isnan(ours["ssim"])
+    for k, v in ref.items():
+        assert abs(ours[k] - v) < tol, (k, ours[k], v)
+
+
+@pytest.mark.parametrize("shape,scale", [((2, 16, 1, 32, 32), 85.0), ((1, 16, 1, 128, 128), 85.0), ((2, 3, 1, 40, 72), 60.0)])
+def test_metric_suite_matches_oracle(shape, scale):
+    from p2igan_b200.metrics import MetricConfig, RainfallMetricSuite
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(shape, generator=g) ** 2 * scale
+    tgt = torch.rand(shape, generator=g) ** 2 * scale
+    ref = O.MetricSuiteOracle()
+    suite = RainfallMetricSuite(MetricConfig()).to(DEV)
+    for a, b in ((pred, tgt), (tgt.flip(-1), tgt)):
+        ref.update(a, b)
+        suite.update(a.to(DEV), b.to(DEV))
+    _compare(suite.compute(), ref.compute())
+    suite.reset()
+    suite.update(pred.to(DEV), tgt.to(DEV))
+    ref2 = O.MetricSuiteOracle()
+    ref2.update(pred, tgt)
+    _compare(suite.compute(), ref2.compute())
+
+
+def test_metric_suite_reference_golden(golden):
+    from p2igan_b200.metrics import MetricConfig, RainfallMetricSuite
+    frames, _, _ = synth.make_batch(2, 16, 32, 32, 12, 1)
+    pred = golden["g32"]["out"]
+    suite = RainfallMetricSuite(MetricConfig()).to(DEV)
+    suite.update((pred * 85.0).to(DEV), (frames * 85.0).to(DEV))
+    suite.update((frames.flip(1) * 85.0).to(DEV), (frames * 85.0).to(DEV))
+    _compare(suite.compute(), golden["metrics32"])
+
+
+def test_metric_suite_stress_256_and_properties():
+    """BASELINE configs[4] shape (8 events of 20x256x256): identical inputs => perfect scores; the contingency table
+    of every threshold sums to the pixel count."""
+    from p2igan_b200.metrics import MetricConfig, RainfallMetricSuite
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(8, 20, 1, 256, 256, generator=g) ** 3 * 85.0).to(DEV)
+    suite = RainfallMetricSuite(MetricConfig()).to(DEV)
+    suite.update(x, x)
+    m = suite.compute()
+    assert m["mae"] == 0.0 and m["rmse"] == 0.0
+    for thr in ("0.50", "2.00", "4.00", "8.00"):
+        assert abs(m[f"cat_thr{thr}/pod"] - 1.0) < 1e-6 and m[f"cat_thr{thr}/far"] == 0.0
+        for s in (1, 2, 4, 8):
+            assert abs(m[f"fss_thr{thr}_s{s}"] - 1.0) < 1e-6
+    st = suite.state.cpu()
+    for t in range(4):
+        assert float(st[3 + 4 * t:7 + 4 * t].sum()) == 8 * 20 * 256 * 256
+    with pytest.raises(ValueError):
+        RainfallMetricSuite(MetricConfig(scales=(1, 3)))
