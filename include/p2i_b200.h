@@ -195,11 +195,13 @@ typedef struct P2iSnLayer {
     float* sigma;   /* out: u . (W v)                                          */
     float* u_snap;  /* optional copies of the u / v used for sigma (kept for the backward of THIS call, since */
     float* v_snap;  /* the next forward updates weight_u / weight_v in place); may be NULL                    */
+    float* scratch; /* f32 [2 + rows], zero-filled once by the caller (left clean after every call)           */
     int rows, cols;
 } P2iSnLayer;
 /* torch.nn.utils.spectral_norm's pre-forward hook for a table of layers, one launch: training != 0 runs ONE
- * power iteration (v <- normalize(W^T u), u <- normalize(W v), eps 1e-12) before sigma; eval uses stored u, v. */
-int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int training, void* stream);
+ * power iteration (v <- normalize(W^T u), u <- normalize(W v), eps 1e-12) before sigma; eval uses stored u, v.
+ * max_rows / max_cols: the largest rows / cols in the table (grid sizing). */
+int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int max_rows, int max_cols, int training, void* stream);
 
 typedef struct P2iPackLayer {
     const float* W;     /* weight_orig [Cout][Cin][kt][k][k]                                   */

@@ -37,6 +37,7 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Mapping, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -116,10 +117,11 @@ def idw_exact(tz: Tensor, ty: Tensor, tx: Tensor, values: Tensor, shape: Tuple[i
     sw, sh, sd = max(W - 1, 1), max(H - 1, 1), max(D - 1, 1)
     cx, cy, cz = (sh * sd) ** 2, (sw * sd) ** 2, (sw * sh) ** 2
     denom = float(sw * sh * sd)
-    out = torch.empty(Q, dtype=torch.float32)
+    outs = []
     nb = torch.empty(Q, kk, dtype=torch.int64) if return_neighbors else None
     q = torch.arange(Q)
     qz, qy, qx = q // (H * W), (q // W) % H, q % W
+    values_np = values.detach().to(torch.float32).contiguous().numpy()
     for s in range(0, Q, chunk):
         e = min(s + chunk, Q)
         key = (cx * (qx[s:e, None] - tx[None]) ** 2 + cy * (qy[s:e, None] - ty[None]) ** 2
@@ -128,14 +130,20 @@ def idw_exact(tz: Tensor, ty: Tensor, tx: Tensor, values: Tensor, shape: Tuple[i
         comp = key * (1 << 20) + torch.arange(N)[None]
         ck, _ = torch.topk(comp, kk, dim=1, largest=False)
         ik = ck & ((1 << 20) - 1)
-        dk = torch.sqrt((ck >> 20).to(torch.float32)) / denom
-        inv = 1.0 / (dk + tau)
+        # The fp32 weight arithmetic runs in numpy (single-threaded): torch's multi-threaded CPU elementwise/reduction
+        # path was observed to be irreproducible run-to-run (3e-5) on the GPU boxes' 16-core hosts.
+        ck_np, ik_np = ck.numpy(), ik.numpy()
+        dk = np.sqrt((ck_np >> 20).astype(np.float32)) / np.float32(denom)
+        inv = np.float32(1.0) / (dk + np.float32(tau))
         w = inv * inv
-        w = w / (w.sum(dim=1, keepdim=True) + 1e-12)
-        out[s:e] = (values[ik] * w).sum(dim=1)
+        w = w / (w.sum(axis=1, keepdims=True, dtype=np.float32) + np.float32(1e-12))
+        if values.requires_grad:       # autograd path (training-step oracle): linear in `values`
+            outs.append((values[ik] * torch.from_numpy(w)).sum(dim=1))
+        else:
+            outs.append(torch.from_numpy((values_np[ik_np] * w).sum(axis=1, dtype=np.float32)))
         if nb is not None:
             nb[s:e] = ik
-    out = out.reshape(D, H, W)
+    out = torch.cat(outs).reshape(D, H, W)
     return (out, nb) if return_neighbors else out
 
 

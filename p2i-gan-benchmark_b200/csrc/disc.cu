@@ -21,61 +21,80 @@ __device__ __forceinline__ float blk_sum(float v, float* sh) {   // result valid
 }
 
 // ------------------------------------------------------------------------------------------------
-// Spectral norm: one block per layer.  training: v <- normalize(W^T u); u <- normalize(W v) (in place, eps 1e-12);
-// sigma = u . (W v).  eval: sigma from the stored u, v.
+// Spectral norm (torch.nn.utils.spectral_norm pre-forward hook), all layers in three grid-parallel launches:
+//   K1  t1 = W^T u            (training only)     ss1 += |t1|^2
+//   K2  t2' = W t1  (eval: W v)                   ss2 += |t2'|^2
+//   K3  n1 = max(|t1|,eps); v = t1/n1; t2 = t2'/n1; n2 = max(|t2|,eps); u = t2/n2; sigma = u . t2   (eval: sigma = u . t2')
+// scratch per layer: [0] ss1, [1] ss2, [2 .. 2+rows) t2'   (K3 leaves ss1, ss2 at zero for the next call)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) spectral_norm_kernel(const P2iSnLayer* __restrict__ table, int training) {
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const P2iSnLayer* __restrict__ table) {
+    const P2iSnLayer L = table[blockIdx.y];
+    __shared__ float sh[32];
+    const int R = L.rows, K = L.cols;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= K) return;
+    float s = 0.f;
+    if (j < K) {
+        for (int i = 0; i < R; ++i) s = fmaf(L.W[static_cast<size_t>(i) * K + j], L.u[i], s);
+        L.v[j] = s;                                   // un-normalised; K3 divides by n1
+    }
+    const float ss = blk_sum(j < K ? s * s : 0.f, sh);
+    if (threadIdx.x == 0) atomicAdd(&L.scratch[0], ss);
+}
+
+__global__ void __launch_bounds__(256) sn_wv_kernel(const P2iSnLayer* __restrict__ table) {
+    const P2iSnLayer L = table[blockIdx.y];
+    const int R = L.rows, K = L.cols;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= R) return;
+    float s = 0.f;
+    for (int j = lane; j < K; j += 32) s = fmaf(L.W[static_cast<size_t>(i) * K + j], L.v[j], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        L.scratch[2 + i] = s;
+        atomicAdd(&L.scratch[1], s * s);
+    }
+}
+
+__global__ void __launch_bounds__(256) sn_finish_kernel(const P2iSnLayer* __restrict__ table, int training) {
     const P2iSnLayer L = table[blockIdx.x];
     __shared__ float sh[32];
-    __shared__ float t2[512];
     const int R = L.rows, K = L.cols;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (training) {
-        float ss = 0.f;
-        for (int j = threadIdx.x; j < K; j += blockDim.x) {
-            float s = 0.f;
-            for (int i = 0; i < R; ++i) s = fmaf(L.W[static_cast<size_t>(i) * K + j], L.u[i], s);
-            L.v[j] = s;
-            ss += s * s;
-        }
-        ss = blk_sum(ss, sh);
-        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-        for (int j = threadIdx.x; j < K; j += blockDim.x) L.v[j] *= inv;
-        __threadfence_block();
-        __syncthreads();
-    }
-    if (L.v_snap)
-        for (int j = threadIdx.x; j < K; j += blockDim.x) L.v_snap[j] = L.v[j];
-    for (int i = warp; i < R; i += 32) {
-        float s = 0.f;
-        for (int j = lane; j < K; j += 32) s = fmaf(L.W[static_cast<size_t>(i) * K + j], L.v[j], s);
-        s = warp_sum(s);
-        if (lane == 0) t2[i] = s;
-    }
-    __syncthreads();
     float sigma;
     if (training) {
-        float ss = 0.f;
-        for (int i = threadIdx.x; i < R; i += blockDim.x) ss += t2[i] * t2[i];
-        ss = blk_sum(ss, sh);
-        const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+        const float n1 = fmaxf(sqrtf(L.scratch[0]), 1e-12f);
+        const float n2 = fmaxf(sqrtf(L.scratch[1]) / n1, 1e-12f);
+        for (int j = threadIdx.x; j < K; j += blockDim.x) {
+            const float vn = L.v[j] / n1;
+            L.v[j] = vn;
+            if (L.v_snap) L.v_snap[j] = vn;
+        }
         float dot = 0.f;
         for (int i = threadIdx.x; i < R; i += blockDim.x) {
-            const float un = t2[i] / nrm;
+            const float t2 = L.scratch[2 + i] / n1;
+            const float un = t2 / n2;
             L.u[i] = un;
             if (L.u_snap) L.u_snap[i] = un;
-            dot += un * t2[i];
+            dot += un * t2;
         }
         sigma = blk_sum(dot, sh);
     } else {
         float dot = 0.f;
         for (int i = threadIdx.x; i < R; i += blockDim.x) {
-            dot += L.u[i] * t2[i];
+            dot += L.u[i] * L.scratch[2 + i];
             if (L.u_snap) L.u_snap[i] = L.u[i];
         }
+        if (L.v_snap)
+            for (int j = threadIdx.x; j < K; j += blockDim.x) L.v_snap[j] = L.v[j];
         sigma = blk_sum(dot, sh);
     }
-    if (threadIdx.x == 0) *L.sigma = sigma;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *L.sigma = sigma;
+        L.scratch[0] = 0.f;
+        L.scratch[1] = 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -157,11 +176,10 @@ __global__ void __launch_bounds__(128) d3d_first_fwd_kernel(const float* __restr
     if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long total = static_cast<long long>(B) * T * Ho * Wo;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int total = B * T * Ho * Wo;          // < 2^31 (checked on the host)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int xo = static_cast<int>(idx % Wo), yo = static_cast<int>((idx / Wo) % Ho);
-    const int t = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % T), b = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho * T));
+    const int xo = idx % Wo, r1 = idx / Wo, yo = r1 % Ho, r2 = r1 / Ho, t = r2 % T, b = r2 / T;
     float in[27];
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt)
@@ -293,10 +311,17 @@ __global__ void __launch_bounds__(256) disc_tail_fuse_kernel(const float* __rest
 
 using namespace p2i;
 
-extern "C" int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int training, void* stream) {
-    P2I_CHECK_ARG(table_dev && n_layers > 0, "spectral_norm: empty table");
-    spectral_norm_kernel<<<n_layers, 1024, 0, as_stream(stream)>>>(table_dev, training);
-    P2I_CHECK_LAUNCH("spectral_norm_kernel");
+extern "C" int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int max_rows, int max_cols, int training,
+                                 void* stream) {
+    P2I_CHECK_ARG(table_dev && n_layers > 0 && max_rows > 0 && max_cols > 0, "spectral_norm: bad arguments");
+    if (training) {
+        sn_wtu_kernel<<<dim3(cdiv(max_cols, 256), n_layers), 256, 0, as_stream(stream)>>>(table_dev);
+        P2I_CHECK_LAUNCH("sn_wtu_kernel");
+    }
+    sn_wv_kernel<<<dim3(cdiv(max_rows, 8), n_layers), 256, 0, as_stream(stream)>>>(table_dev);
+    P2I_CHECK_LAUNCH("sn_wv_kernel");
+    sn_finish_kernel<<<n_layers, 256, 0, as_stream(stream)>>>(table_dev, training);
+    P2I_CHECK_LAUNCH("sn_finish_kernel");
     return P2I_OK;
 }
 
@@ -321,6 +346,7 @@ extern "C" int p2i_d3d_first_fwd(const float* x, const float* w, const float* si
                                  int H, int W, void* stream) {
     P2I_CHECK_ARG(x && w && sigma && bias && y, "d3d_first_fwd: null pointer");
     P2I_CHECK_ARG(H % 4 == 0 && W % 4 == 0, "d3d_first_fwd: H, W must be multiples of 4");
+    P2I_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 31), "d3d_first_fwd: tensor too large for 32-bit indexing");
     const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
     d3d_first_fwd_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, as_stream(stream)>>>(
         x, w, sigma, bias, static_cast<__nv_bfloat16*>(y), B, T, H, W);

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(192) d3d_first_bwd_w_kernel(const __nv_bfloat1
     __syncthreads();
     const int kt = threadIdx.x % 3, cq = (threadIdx.x / 3) & 3, s = threadIdx.x / 12;
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long total = static_cast<long long>(B) * T * Ho * Wo;
+    const int total = B * T * Ho * Wo;          // < 2^31 (checked on the host)
     float acc[8][9];
     float bsum[8];
 #pragma unroll
@@ -213,10 +213,9 @@ __global__ void __launch_bounds__(192) d3d_first_bwd_w_kernel(const __nv_bfloat1
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
     }
-    for (long long idx = static_cast<long long>(blockIdx.x) * 16 + s; idx < total; idx += static_cast<long long>(gridDim.x) * 16) {
-        const int xo = static_cast<int>(idx % Wo), yo = static_cast<int>((idx / Wo) % Ho);
-        const int t = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % T), b = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho * T));
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(dpre + idx * 32 + cq * 8));
+    for (int idx = blockIdx.x * 16 + s; idx < total; idx += gridDim.x * 16) {
+        const int xo = idx % Wo, r1 = idx / Wo, yo = r1 % Ho, r2 = r1 / Ho, t = r2 % T, b = r2 / T;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(dpre + static_cast<size_t>(idx) * 32 + cq * 8));
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
         float g[8];
 #pragma unroll
@@ -260,11 +259,10 @@ __global__ void __launch_bounds__(128) d3d_first_bwd_x_kernel(const __nv_bfloat1
     for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) sw[i] = w[i] * inv;
     __syncthreads();
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long total = static_cast<long long>(B) * T * H * W;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int total = B * T * H * W;            // < 2^31 (checked on the host)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int xx = static_cast<int>(idx % W), yy = static_cast<int>((idx / W) % H);
-    const int t = static_cast<int>((idx / (static_cast<long long>(W) * H)) % T), b = static_cast<int>(idx / (static_cast<long long>(W) * H * T));
+    const int xx = idx % W, r1 = idx / W, yy = r1 % H, r2 = r1 / H, t = r2 % T, b = r2 / T;
     float acc = 0.f;
     for (int kt = 0; kt < 3; ++kt) {
         const int to = t - kt + 1;
@@ -397,6 +395,7 @@ extern "C" int p2i_colsum_bf16(const void* g, float* out, long long rows, int C,
 extern "C" int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* w, const float* sigma, float* dW, float* db,
                                  float* dx, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dpre && x && w && sigma, "d3d_first_bwd: null pointer");
+    P2I_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 31), "d3d_first_bwd: tensor too large for 32-bit indexing");
     if (dW && db) {
         const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
         long long blocks = (total + 15) / 16;

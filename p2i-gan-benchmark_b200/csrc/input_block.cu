@@ -125,29 +125,39 @@ __global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const i
     }
 }
 
-// Backward of the two gates for the single output channel t that feeds `vals`.
-__global__ void gate_points_bwd_kernel(const float* __restrict__ masked, const int* __restrict__ pts,
-                                       const int* __restrict__ counts, int cap, const float* __restrict__ w0,
-                                       const float* __restrict__ b0, const float* __restrict__ w1,
-                                       const float* __restrict__ b1, const float* __restrict__ dvals,
-                                       float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
-                                       float* __restrict__ db1, int HW) {
+// Backward of the two gates for the single output channel t that feeds `vals`.  Per-point contributions are reduced
+// with warp shuffles first (points are sorted by frame, so a warp almost always shares t), then one shared-memory and
+// one global atomic per weight per block.
+__global__ void __launch_bounds__(128) gate_points_bwd_kernel(const float* __restrict__ masked, const int* __restrict__ pts,
+                                                              const int* __restrict__ counts, int cap, const float* __restrict__ w0,
+                                                              const float* __restrict__ b0, const float* __restrict__ w1,
+                                                              const float* __restrict__ b1, const float* __restrict__ dvals,
+                                                              float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
+                                                              float* __restrict__ db1, int HW) {
     __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
     __shared__ float aw0[256], aw1[256], ab0[16], ab1[16];
-    if (static_cast<int>(blockIdx.x * blockDim.x) >= counts[blockIdx.y]) return;   // no observed point in this block
+    const int b = blockIdx.y;
+    const int n = counts[b];
+    if (static_cast<int>(blockIdx.x * blockDim.x) >= n) return;   // no observed point in this block
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; aw0[i] = 0.f; aw1[i] = 0.f; }
     if (threadIdx.x < 16) {
         sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x];
         ab0[threadIdx.x] = 0.f; ab1[threadIdx.x] = 0.f;
     }
     __syncthreads();
-    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < counts[b]) {
+    const bool active = i < n;
+    float x[16], h[16], dg0[16];
+    float dg1 = 0.f;
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { x[k] = 0.f; h[k] = 0.f; dg0[k] = 0.f; }
+    if (active) {
         const int p = pts[static_cast<size_t>(b) * cap + i];
-        const int t = p / HW, pix = p - t * HW;
+        t = p / HW;
+        const int pix = p - t * HW;
         const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
-        float x[16], h[16], g0[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = xin[static_cast<size_t>(k) * HW];
 #pragma unroll
@@ -155,7 +165,6 @@ __global__ void gate_points_bwd_kernel(const float* __restrict__ masked, const i
             float g = sb0[j];
 #pragma unroll
             for (int k = 0; k < 16; ++k) g = fmaf(sw0[j * 16 + k], x[k], g);
-            g0[j] = g;
             h[j] = fmaxf(fmaf(x[j], g, x[j]), 0.f);
         }
         float g1 = sb1[t];
@@ -164,32 +173,42 @@ __global__ void gate_points_bwd_kernel(const float* __restrict__ masked, const i
         float ht = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) ht = (k == t) ? h[k] : ht;
-        const float pre = fmaf(ht, g1, ht);
         float dv = dvals[static_cast<size_t>(b) * cap + i];
-        if (pre <= 0.f) dv = 0.f;
-        if (dv != 0.f) {
-            // v = ht*(1+g1):  d g1 = dv*ht ; d ht += dv*(1+g1) ; g1 = b1[t] + sum_k w1[t,k] h[k]
-            const float dg1 = dv * ht;
-            atomicAdd(&ab1[t], dg1);
-            float dh[16];
+        if (fmaf(ht, g1, ht) <= 0.f) dv = 0.f;
+        // v = ht*(1+g1): d g1 = dv*ht ; d h[k] = dg1*w1[t,k] (+ dv*(1+g1) for k == t) ; h[j] = relu(x[j]*(1+g0[j]))
+        dg1 = dv * ht;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                atomicAdd(&aw1[t * 16 + k], dg1 * h[k]);
-                dh[k] = dg1 * sw1[t * 16 + k] + ((k == t) ? dv * (1.f + g1) : 0.f);
-            }
-            // h[j] = relu(x[j]*(1+g0[j])) : d g0[j] = dh[j]*x[j] when active
+        for (int k = 0; k < 16; ++k) {
+            const float dh = dg1 * sw1[t * 16 + k] + ((k == t) ? dv * (1.f + g1) : 0.f);
+            dg0[k] = (h[k] > 0.f) ? dh * x[k] : 0.f;
+        }
+    }
+    // layer 2 (row t of w1): warp-uniform t -> shuffle reduction, else per-lane atomics
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    const int t0 = __shfl_sync(0xffffffffu, t, act ? (__ffs(act) - 1) : 0);
+    if (__all_sync(0xffffffffu, !active || t == t0)) {
+        const float s = warp_sum(dg1);
+        if (lane == 0 && s != 0.f) atomicAdd(&ab1[t0], s);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (h[j] > 0.f && dh[j] != 0.f) {
-                    const float dg0 = dh[j] * x[j];
-                    if (dg0 != 0.f) {
-                        atomicAdd(&ab0[j], dg0);
+        for (int k = 0; k < 16; ++k) {
+            const float r = warp_sum(dg1 * h[k]);
+            if (lane == 0 && r != 0.f) atomicAdd(&aw1[t0 * 16 + k], r);
+        }
+    } else if (active && dg1 != 0.f) {
+        atomicAdd(&ab1[t], dg1);
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (x[k] != 0.f) atomicAdd(&aw0[j * 16 + k], dg0 * x[k]);
-                    }
-                }
-            }
+        for (int k = 0; k < 16; ++k) atomicAdd(&aw1[t * 16 + k], dg1 * h[k]);
+    }
+    // layer 1: dw0[j][k] = sum dg0[j]*x[k], db0[j] = sum dg0[j]
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float s = warp_sum(dg0[j]);
+        if (__all_sync(0xffffffffu, dg0[j] == 0.f)) continue;
+        if (lane == 0) atomicAdd(&ab0[j], s);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float r = warp_sum(dg0[j] * x[k]);
+            if (lane == 0 && r != 0.f) atomicAdd(&aw0[j * 16 + k], r);
         }
     }
     __syncthreads();

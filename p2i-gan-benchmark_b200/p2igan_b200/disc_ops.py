@@ -70,12 +70,16 @@ class _OperandSet:
         self.u = {n: torch.empty_like(mods[n].weight_u) for n in ALL_SN}
         self.v = {n: torch.empty_like(mods[n].weight_v) for n in ALL_SN}
         sn = b""
+        self.sn_scratch = torch.zeros(len(ALL_SN), 2 + 512, dtype=torch.float32, device=dev)
+        self.max_rows = self.max_cols = 1
         for i, n in enumerate(ALL_SN):
             m = mods[n]
             rows = m.weight_orig.shape[0]
             cols = m.weight_orig.numel() // rows
-            sn += struct.pack("<QQQQQQii", m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
-                              self.sigma[i:i + 1].data_ptr(), self.u[n].data_ptr(), self.v[n].data_ptr(), rows, cols)
+            self.max_rows, self.max_cols = max(self.max_rows, rows), max(self.max_cols, cols)
+            sn += struct.pack("<QQQQQQQii", m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
+                              self.sigma[i:i + 1].data_ptr(), self.u[n].data_ptr(), self.v[n].data_ptr(),
+                              self.sn_scratch[i].data_ptr(), rows, cols)
         self.sn_table = torch.frombuffer(bytearray(sn), dtype=torch.uint8).to(dev)
         self.w: Dict[str, torch.Tensor] = {}
         self.wt: Dict[str, torch.Tensor] = {}
@@ -136,7 +140,7 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     mods = state.mods
     dev = x.device
     xf = x.detach().reshape(B, T, H, W).contiguous().float()
-    LIB.call("p2i_spectral_norm", ptr(st.sn_table), len(ALL_SN), 1 if D.training else 0, stream())
+    LIB.call("p2i_spectral_norm", ptr(st.sn_table), len(ALL_SN), st.max_rows, st.max_cols, 1 if D.training else 0, stream())
     LIB.call("p2i_disc_pack_weights", ptr(st.pack_table), len(TC_LAYERS), stream())
     bf = torch.bfloat16
     bias = {n: mods[n].bias.detach() for n in ALL_SN}
