@@ -141,6 +141,11 @@ typedef struct P2iConvDesc {
 int p2i_conv_igemm(const void* x, const void* w, const P2iConvDesc* desc, const void* residual, const void* mask,
                    const float* bias, void* y, void* stream);
 int p2i_conv_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc* desc, void* stream);
+/* Kernel selection for p2i_conv_igemm / p2i_conv2d_igemm_fwd (A/B measurements and tests): 0 = automatic (the halo
+ * kernel of conv_igemm_halo.cu when the shape is eligible, else the first-generation kernel), 1 = first generation
+ * only, 2 = halo only (ineligible shapes fail with P2I_ERR_INVALID), 3 / 4 = halo only, forced to single CTAs /
+ * CTA pairs (tcgen05 cta_group::2). */
+int p2i_set_conv_impl(int impl);
 
 /* Weight gradient: dW[tap][co][ci] += sum_pix dy[pix][co] * x[pix+tap][ci]  (fp32 [k*k][Cout][Cin], atomically
  * accumulated: the caller zero-fills).  x [B,H,W,Cin], dy [B,H,W,Cout] bf16.  Cin in {64} or % 128 == 0. */

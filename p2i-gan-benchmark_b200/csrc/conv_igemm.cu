@@ -328,6 +328,14 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const __
     }
 }
 
+// conv_igemm_halo.cu: second-generation kernel (single halo box per tile, resident / M-blocked weights, TMA-store
+// epilogue).  Returns +1 when the shape is not eligible.
+int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const void* residual, const void* mask,
+                   const float* bias, void* y, void* stream);
+
+int set_halo_cg(int cg);
+static std::atomic<int> g_conv_impl{0};   // 0 auto (halo when eligible), 1 legacy only, 2 halo only (3: single CTA, 4: CTA pairs)
+
 static int run_igemm(const void* x, const void* w, const P2iConvDesc& d, const void* residual, const void* mask,
                      const float* bias, void* y, void* stream) {
     P2I_CHECK_ARG(x && w && y, "conv_igemm: null pointer");
@@ -341,6 +349,12 @@ static int run_igemm(const void* x, const void* w, const P2iConvDesc& d, const v
     P2I_CHECK_ARG(d.mask_mode == 0 || mask, "conv_igemm: mask_mode set without a mask");
     P2I_CHECK_ARG(d.out_mode != 1 || (d.H % 2 == 0 && d.W % 2 == 0), "conv_igemm: s2d pack needs even H, W");
     P2I_CHECK_ARG(d.out_mode != 2 || (d.Cout % 256 == 0 || (d.Cout / 4) % 16 == 0), "conv_igemm: s2d unpack needs Cout/4 %% 16 == 0");
+    const int impl = g_conv_impl.load(std::memory_order_relaxed);
+    if (impl != 1) {
+        const int rc = run_igemm_halo(x, w, d, residual, mask, bias, y, stream);
+        if (rc <= 0) return rc;
+        if (impl == 2) return fail(P2I_ERR_INVALID, "conv_igemm: shape not eligible for the halo kernel");
+    }
     ConvParams p;
     p.F = d.samples * d.T_out; p.T_out = d.T_out; p.T_in = d.T_in;
     p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout;
@@ -384,6 +398,13 @@ static int run_igemm(const void* x, const void* w, const P2iConvDesc& d, const v
 }  // namespace p2i
 
 using namespace p2i;
+
+extern "C" int p2i_set_conv_impl(int impl) {
+    P2I_CHECK_ARG(impl >= 0 && impl <= 4, "set_conv_impl: 0 auto | 1 legacy | 2 halo | 3 halo single-CTA | 4 halo CTA pairs");
+    set_halo_cg(impl == 3 ? 1 : (impl == 4 ? 2 : 0));
+    g_conv_impl.store(impl >= 2 ? 2 : impl);
+    return P2I_OK;
+}
 
 extern "C" int p2i_conv_igemm(const void* x, const void* w, const P2iConvDesc* desc, const void* residual, const void* mask,
                               const float* bias, void* y, void* stream) {

@@ -18,6 +18,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math"]
 # --use_fast_math would change division/sqrt rounding in the parity-sensitive kernels: keep IEEE there.
 NVCC_FLAGS.remove("--use_fast_math")
+if os.environ.get("P2I_HALO_PROF"):      # diagnostics build: the halo conv kernel prints per-role wait cycles
+    NVCC_FLAGS.append("-DHALO_PROF")
 
 
 def _digest(paths):
