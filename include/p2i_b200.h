@@ -62,7 +62,15 @@ int p2i_gate_points_bwd(const float* masked, const int* pts, const int* counts, 
  * reused when search == 0, e.g. while the mask is unchanged between steps).
  * Samples with zero points give zeros (layer.py:330-332). */
 int p2i_idw_knn_fwd(const int* pts, const float* vals, const int* counts, const int* src, int cap, float* out,
-                    int* nbr_idx, float* nbr_w, int B, int T, int H, int W, float tau, int search, void* stream);
+                    int* nbr_idx, float* nbr_w, int B, int T, int H, int W, float tau, int search, const int* reuse_flag,
+                    int* cache_idx, float* cache_w, void* stream);
+/* Device-side cache of sample 0's neighbour table across calls (a static gauge mask makes every step search the same
+ * pattern; the reference recomputes cdist + topk every forward, layer.py:280-281).  Compares sample 0's points with
+ * cache_pts [cap] / cache_count [1]; writes flag[0] = 1 when identical, else 0 and replaces the cached points.  With
+ * reuse_flag / cache_idx [T*H*W,4] / cache_w passed to p2i_idw_knn_fwd (all three may be NULL), sample 0's rows of
+ * the table are copied from the cache when flag[0] == 1, else searched and stored into the cache.  No host sync. */
+int p2i_idw_cache_check(const int* pts, const int* counts, int cap, int* cache_pts, int* cache_count, int* flag,
+                        void* stream);
 /* dvals[b, idx] += w * dout ; dvals [B,cap] must be zero-initialised. */
 int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const float* nbr_w, const int* counts, const int* src,
                     float* dvals, int cap, int B, int T, int H, int W, void* stream);
@@ -314,8 +322,10 @@ typedef struct P2iAdamTensor {
     long long n;
 } P2iAdamTensor;
 /* One launch for a whole model.  chunks_dev: int pairs (tensor index, chunk index), chunk = p2i_adam_chunk_elems()
- * elements.  *step_dev (device float) is incremented first and drives the bias corrections, so the call is CUDA-graph
- * capturable.  grad_scale multiplies every gradient (1/world_size when the gradients hold a SUM over ranks). */
+ * elements.  step_dev points to THREE device floats {step, lr/(1-beta1^step), 1/sqrt(1-beta2^step)}: step is
+ * incremented first and the two bias-correction factors are refreshed from it by a one-thread kernel (double
+ * precision, as torch does on the host), so the call is CUDA-graph capturable and the update kernel's blocks only
+ * read them.  grad_scale multiplies every gradient (1/world_size when the gradients hold a SUM over ranks). */
 int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 int p2i_adam_chunk_elems(void);

@@ -6,22 +6,22 @@
 
 namespace p2i {
 
-constexpr int ADAM_CHUNK = 16384;
+constexpr int ADAM_CHUNK = 8192;
 
-__global__ void adam_tick_kernel(float* step) { *step += 1.f; }
+// step[0] += 1; step[1] = lr / (1 - beta1^t); step[2] = 1 / sqrt(1 - beta2^t)
+__global__ void adam_tick_kernel(float* step, float lr, float beta1, float beta2) {
+    const float t = step[0] + 1.f;
+    step[0] = t;
+    const double st = static_cast<double>(t);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), st), bc2 = 1.0 - pow(static_cast<double>(beta2), st);
+    step[1] = static_cast<float>(static_cast<double>(lr) / bc1);
+    step[2] = static_cast<float>(1.0 / sqrt(bc2));
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(const P2iAdamTensor* __restrict__ tensors, const int2* __restrict__ chunks,
                                                    const float* __restrict__ step_dev, float lr, float beta1, float beta2, float eps,
                                                    float grad_scale) {
-    __shared__ float s_c[2];
-    if (threadIdx.x == 0) {                           // bias corrections from the device-resident step counter
-        const double st = static_cast<double>(*step_dev);
-        const double bc1 = 1.0 - pow(static_cast<double>(beta1), st), bc2 = 1.0 - pow(static_cast<double>(beta2), st);
-        s_c[0] = static_cast<float>(static_cast<double>(lr) / bc1);
-        s_c[1] = static_cast<float>(1.0 / sqrt(bc2));
-    }
-    __syncthreads();
-    const float lr_over_bc1 = s_c[0], inv_sqrt_bc2 = s_c[1];
+    const float lr_over_bc1 = __ldg(step_dev + 1), inv_sqrt_bc2 = __ldg(step_dev + 2);
     const int2 ch = chunks[blockIdx.x];               // (tensor index, chunk index)
     const P2iAdamTensor t = tensors[ch.x];
     const long long start = static_cast<long long>(ch.y) * ADAM_CHUNK;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const P2iAdamTensor* __restri
 extern "C" int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
                              float beta1, float beta2, float eps, float grad_scale, void* stream) {
     P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step_dev, "adam_step: bad arguments");
-    p2i::adam_tick_kernel<<<1, 1, 0, p2i::as_stream(stream)>>>(step_dev);
+    p2i::adam_tick_kernel<<<1, 1, 0, p2i::as_stream(stream)>>>(step_dev, lr, beta1, beta2);
     P2I_CHECK_LAUNCH("adam_tick_kernel");
     p2i::adam_kernel<<<n_chunks, 256, 0, p2i::as_stream(stream)>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev), step_dev, lr,
                                                                    beta1, beta2, eps, grad_scale);

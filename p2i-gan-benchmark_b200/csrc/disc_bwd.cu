@@ -171,8 +171,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     const long long stride = (static_cast<long long>(gridDim.x) * blockDim.x / cg) * cg;
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int c8 = static_cast<int>(i % cg);
-    if (i < stride) {
-        for (; i < total; i += stride) {
+    const bool live = i < stride;
+    {
+        for (; live && i < total; i += stride) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(g) + i);
             const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -182,6 +183,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
                 acc[2 * k + 1] += f.y;
             }
         }
+    }
+    // lanes l, l+cg, l+2cg.. of a warp hold the same channel group when cg < 32 (the stride is a multiple of cg and
+    // blockDim of 32): fold them with shuffles so that at most one lane per (warp, channel) touches shared memory
+    const bool fold = (cg & (cg - 1)) == 0 && cg < 32;      // power-of-two group count: lane ^ off keeps the group
+    if (fold)
+        for (int off = 16; off >= cg; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        }
+    if (!fold || (threadIdx.x & 31) < cg) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[c8 * 8 + k], acc[k]);
     }
@@ -292,6 +303,255 @@ __global__ void __launch_bounds__(128) d3d_first_bwd_x_kernel(const __nv_bfloat1
     dx[idx] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Register-blocked variants of the thin-layer backward kernels.  Reductions go warp-shuffle -> one shared-memory
+// pass -> one global atomic per (block, element): shared-memory float atomics are CAS loops and serialise badly.
+// ------------------------------------------------------------------------------------------------
+
+// d2d.8 backward, C == 256: lane l owns channels 8l..8l+7 (weights and dW accumulators in registers), warps stride
+// over pixels.
+__global__ void __launch_bounds__(256) d2d_last_bwd256_kernel(const float* __restrict__ d_o, const __nv_bfloat16* __restrict__ y4,
+                                                              const float* __restrict__ w, const float* __restrict__ sigma,
+                                                              __nv_bfloat16* __restrict__ dpre, float* __restrict__ dW,
+                                                              float* __restrict__ db, int B, int H, int W) {
+    constexpr int C = 256;
+    __shared__ float sdw[9 * C];
+    __shared__ float sdb[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv = 1.f / *sigma;
+    float wr[9][8], aw[9][8];
+    {
+        const float* wp = w + lane * 72;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { wr[t][i] = __ldg(wp + i * 9 + t) * inv; aw[t][i] = 0.f; }
+    }
+    float bsum = 0.f;
+    const int npix = B * H * W;
+    const int nwarps = gridDim.x * 8;
+    for (int pix = blockIdx.x * 8 + warp; pix < npix; pix += nwarps) {
+        const int xx = pix % W, yy = (pix / W) % H;
+        float g[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int oy = yy - ky + 1, ox = xx - kx + 1;
+                g[ky * 3 + kx] = (oy >= 0 && oy < H && ox >= 0 && ox < W) ? __ldg(d_o + pix - (ky - 1) * W - (kx - 1)) : 0.f;
+            }
+        bsum += g[4];
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(y4 + static_cast<size_t>(pix) * C) + lane);
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t2 = unpack_bf16x2(qq[i]);
+            f[2 * i] = t2.x; f[2 * i + 1] = t2.y;
+        }
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                s = fmaf(g[t], wr[t][i], s);
+                aw[t][i] = fmaf(g[t], f[i], aw[t][i]);
+            }
+            a[i] = s * (f[i] > 0.f ? 1.f : 0.2f);
+        }
+        reinterpret_cast<uint4*>(dpre + static_cast<size_t>(pix) * C)[lane] =
+            make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+    }
+    if (!dW) return;
+    // block reduction of the 8 warps: each warp adds its registers into shared memory in turn
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sdw[i] = 0.f;
+    if (lane == 0) sdb[warp] = bsum;
+    __syncthreads();
+    for (int wv = 0; wv < 8; ++wv) {
+        if (warp == wv) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) sdw[lane * 72 + i * 9 + t] += aw[t][i];
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x)
+        if (sdw[i] != 0.f) atomicAdd(&dW[i], sdw[i]);
+    if (threadIdx.x == 0 && db) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sdb[i];
+        atomicAdd(db, s);
+    }
+}
+
+// d3d.0 weight gradient, W % 8 == 0.  Warp = 8 groups of 4 consecutive output pixels (lane >> 2) x 4 channel octets
+// (lane & 3); the warp's temporal tap is warp % 3.  72 accumulators (8 channels x 9 spatial taps) per thread.
+__global__ void __launch_bounds__(192) d3d_first_bwd_w4_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ x,
+                                                               float* __restrict__ dW, float* __restrict__ db, int B, int T, int H, int W) {
+    __shared__ float sdw[32 * 27], sdb[32];
+    for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) sdw[i] = 0.f;
+    if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kt = warp % 3, half = warp / 3;
+    const int cq = lane & 3, gl = lane >> 2;
+    const int Ho = H >> 1, Wo = W >> 1, Wg = Wo >> 2;
+    const int ngroups = B * T * Ho * Wg;
+    float acc[8][9], bsum[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        bsum[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
+    }
+    for (int g0 = (blockIdx.x * 2 + half) * 8; g0 < ngroups; g0 += gridDim.x * 16) {
+        const int gid = g0 + gl;
+        if (gid >= ngroups) continue;
+        const int j = gid % Wg, r1 = gid / Wg, yo = r1 % Ho, r2 = r1 / Ho, t = r2 % T, b = r2 / T;
+        const int ti = t + kt - 1;
+        const bool tok = ti >= 0 && ti < T;
+        if (!tok && kt != 0) continue;
+        const uint4* gp = reinterpret_cast<const uint4*>(dpre + static_cast<size_t>(gid) * 128 + cq * 8);   // 4 pixels x 32 ch
+        float v[3][9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yi = 2 * yo + ky - 1;
+            if (tok && yi >= 0 && yi < H) {
+                const float* row = x + ((static_cast<size_t>(b) * T + ti) * H + yi) * W + 8 * j;
+                v[ky][0] = (j > 0) ? __ldg(row - 1) : 0.f;
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(row)), q1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
+                v[ky][1] = q0.x; v[ky][2] = q0.y; v[ky][3] = q0.z; v[ky][4] = q0.w;
+                v[ky][5] = q1.x; v[ky][6] = q1.y; v[ky][7] = q1.z; v[ky][8] = q1.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) v[ky][k] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint4 q = __ldg(gp + p * 4);
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+            float g[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(qq[k]);
+                g[2 * k] = f.x; g[2 * k + 1] = f.y;
+            }
+            if (kt == 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bsum[c] += g[c];
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c][ky * 3 + kx] = fmaf(g[c], v[ky][2 * p + kx], acc[c][ky * 3 + kx]);
+        }
+    }
+    // reduce over the 8 pixel groups of the warp (lane bits 2..4), then one shared-memory add per (warp, element)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float a = acc[c][k];
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            acc[c][k] = a;
+        }
+        float s = bsum[c];
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        bsum[c] = s;
+    }
+    for (int h = 0; h < 2; ++h) {               // the two warps that share a temporal tap take turns
+        if (half == h && gl == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sdw[(cq * 8 + c) * 27 + kt * 9 + k] += acc[c][k];
+                if (kt == 0) sdb[cq * 8 + c] += bsum[c];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x)
+        if (sdw[i] != 0.f) atomicAdd(&dW[i], sdw[i]);
+    if (threadIdx.x < 32 && sdb[threadIdx.x] != 0.f) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
+}
+
+// d3d.0 input gradient (transposed stride-2 conv), W % 4 == 0: thread = two adjacent 2x2 blocks of dx, i.e. rows
+// 2m, 2m+1 and columns 4j .. 4j+3, fed by the 2 x 3 gradient pixels (m..m+1, 2j..2j+2) of three frames.  Weights are
+// read as broadcast LDS.128 ([kt][c][12] layout), 18 FMAs per 3 shared-memory reads.
+__global__ void __launch_bounds__(128) d3d_first_bwd_x2_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ w,
+                                                               const float* __restrict__ sigma, float* __restrict__ dx, int B, int T, int H, int W) {
+    __shared__ __align__(16) float sw[3 * 32 * 12];
+    const float inv = 1.f / *sigma;
+    for (int i = threadIdx.x; i < 3 * 32 * 12; i += blockDim.x) {
+        const int k = i % 12, c = (i / 12) % 32, kt = i / (12 * 32);
+        sw[i] = (k < 9) ? w[c * 27 + kt * 9 + k] * inv : 0.f;
+    }
+    __syncthreads();
+    const int Ho = H >> 1, Wo = W >> 1, Wp = Wo >> 1;
+    const int total = B * T * Ho * Wp;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = idx % Wp, r1 = idx / Wp, m = r1 % Ho, r2 = r1 / Ho, t = r2 % T, b = r2 / T;
+    float o[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
+    const bool row1 = m + 1 < Ho, col2 = 2 * j + 2 < Wo;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+        const int to = t - kt + 1;
+        if (to < 0 || to >= T) continue;
+        const __nv_bfloat16* base = dpre + (((static_cast<size_t>(b) * T + to) * Ho + m) * Wo + 2 * j) * 32;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float d[2][3][8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const bool ok = (r == 0 || row1) && (cc < 2 || col2);
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) q = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(r) * Wo + cc) * 32 + ch * 8));
+                    const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = unpack_bf16x2(qq[k]);
+                        d[r][cc][2 * k] = f.x; d[r][cc][2 * k + 1] = f.y;
+                    }
+                }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4* wp = reinterpret_cast<const float4*>(sw + (kt * 32 + ch * 8 + c) * 12);
+                const float4 wa = wp[0], wb = wp[1], wc = wp[2];
+                // w[ky][kx]: wa = (00 01 02 10), wb = (11 12 20 21), wc.x = 22
+                const float w00 = wa.x, w01 = wa.y, w02 = wa.z, w10 = wa.w, w11 = wb.x, w12 = wb.y, w20 = wb.z, w21 = wb.w, w22 = wc.x;
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {       // 2x2 block n: gradient columns n, n+1 -> dx columns 2n, 2n+1
+                    const float d00 = d[0][n][c], d01 = d[0][n + 1][c], d10 = d[1][n][c], d11 = d[1][n + 1][c];
+                    o[0][2 * n] = fmaf(d00, w11, o[0][2 * n]);
+                    o[0][2 * n + 1] = fmaf(d00, w12, fmaf(d01, w10, o[0][2 * n + 1]));
+                    o[1][2 * n] = fmaf(d00, w21, fmaf(d10, w01, o[1][2 * n]));
+                    o[1][2 * n + 1] = fmaf(d00, w22, fmaf(d01, w20, fmaf(d10, w02, fmaf(d11, w00, o[1][2 * n + 1]))));
+                }
+            }
+        }
+    }
+    float* op = dx + ((static_cast<size_t>(b) * T + t) * H + 2 * m) * W + 4 * j;
+    *reinterpret_cast<float4*>(op) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    *reinterpret_cast<float4*>(op + W) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+}
+
 // dx[b,c,y,x] += g[b,y,x,c] for c < C (unpacks the padded 64-channel input gradient of d2d.0)
 __global__ void __launch_bounds__(256) disc_unpack_input_grad_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ dx, int C,
                                                                      int HW, long long n) {
@@ -320,19 +580,19 @@ __device__ __forceinline__ size_t packed_index(const P2iSnGrad& L, int co, int c
     return (static_cast<size_t>(tap) * L.Cout + co) * L.cin_pad + ci;
 }
 
-constexpr int SN_BWD_BLOCKS = 32;   // blocks per layer
+constexpr int SN_BWD_BLOCKS = 64;   // blocks per layer
 // pass 1: inner[layer] += <G, W_orig>   pass 2: dW = G/sigma - inner/sigma^2 * u v^T
+// 32-bit index arithmetic throughout (a layer has < 2^31 weights; 64-bit div/mod dominated these kernels).
 __global__ void __launch_bounds__(256) sn_bwd_inner_kernel(const P2iSnGrad* __restrict__ table, float* __restrict__ inner) {
     const P2iSnGrad L = table[blockIdx.y];
     __shared__ float sh[32];
     const int per = L.KT * L.ksize * L.ksize;
     const int K = L.Cin * per;
-    const long long total = static_cast<long long>(L.Cout) * K;
+    const int total = L.Cout * K;
     float acc = 0.f;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int r = static_cast<int>(e % per), ci = static_cast<int>((e / per) % L.Cin), co = static_cast<int>(e / K);
-        acc += L.G[packed_index(L, co, ci, r)] * L.W[e];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int co = e / K, rem = e - co * K, ci = rem / per, r = rem - ci * per;
+        acc = fmaf(L.G[packed_index(L, co, ci, r)], L.W[e], acc);
     }
     acc = blk_sum_all(acc, sh);
     if (threadIdx.x == 0 && acc != 0.f) atomicAdd(&inner[blockIdx.y], acc);
@@ -341,13 +601,12 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const P2iSnGrad* __re
     const P2iSnGrad L = table[blockIdx.y];
     const int per = L.KT * L.ksize * L.ksize;
     const int K = L.Cin * per;
-    const long long total = static_cast<long long>(L.Cout) * K;
+    const int total = L.Cout * K;
     const float sig = *L.sigma;
     const float c1 = 1.f / sig, c2 = inner[blockIdx.y] / (sig * sig);
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int r = static_cast<int>(e % per), ci = static_cast<int>((e / per) % L.Cin), co = static_cast<int>(e / K);
-        L.dW[e] += L.G[packed_index(L, co, ci, r)] * c1 - c2 * L.u[co] * L.v[e - static_cast<long long>(co) * K];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int co = e / K, rem = e - co * K, ci = rem / per, r = rem - ci * per;
+        L.dW[e] += L.G[packed_index(L, co, ci, r)] * c1 - c2 * L.u[co] * L.v[rem];
     }
 }
 
@@ -375,6 +634,14 @@ extern "C" int p2i_d2d_last_bwd(const float* d_out, const void* y4, const float*
                                 float* db, int B, int H, int W, int C, void* stream) {
     P2I_CHECK_ARG(d_out && y4 && w && sigma && dpre, "d2d_last_bwd: null pointer");
     const long long npix = static_cast<long long>(B) * H * W;
+    if (C == 256 && npix < (1ll << 31)) {
+        long long blocks = (npix + 7) / 8;
+        if (blocks > sm_count()) blocks = sm_count();
+        d2d_last_bwd256_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            d_out, static_cast<const __nv_bfloat16*>(y4), w, sigma, static_cast<__nv_bfloat16*>(dpre), dW, db, B, H, W);
+        P2I_CHECK_LAUNCH("d2d_last_bwd256_kernel");
+        return P2I_OK;
+    }
     d2d_last_bwd_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 18 * C * sizeof(float), as_stream(stream)>>>(
         d_out, static_cast<const __nv_bfloat16*>(y4), w, sigma, static_cast<__nv_bfloat16*>(dpre), dW, db, B, H, W, C);
     P2I_CHECK_LAUNCH("d2d_last_bwd_kernel");
@@ -398,14 +665,28 @@ extern "C" int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* 
     P2I_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 31), "d3d_first_bwd: tensor too large for 32-bit indexing");
     if (dW && db) {
         const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
+        if (W % 8 == 0) {
+            long long blocks = (total / 4 + 15) / 16;
+            if (blocks > sm_count() * 2) blocks = sm_count() * 2;
+            d3d_first_bwd_w4_kernel<<<static_cast<unsigned>(blocks), 192, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dpre), x,
+                                                                                                   dW, db, B, T, H, W);
+            P2I_CHECK_LAUNCH("d3d_first_bwd_w4_kernel");
+        } else {
         long long blocks = (total + 15) / 16;
         if (blocks > 148 * 4) blocks = 148 * 4;
         d3d_first_bwd_w_kernel<<<static_cast<unsigned>(blocks), 192, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dpre), x, dW,
                                                                                               db, B, T, H, W);
         P2I_CHECK_LAUNCH("d3d_first_bwd_w_kernel");
+        }
     }
     if (dx) {
         const long long total = static_cast<long long>(B) * T * H * W;
+        if (W % 4 == 0 && H % 2 == 0) {
+            d3d_first_bwd_x2_kernel<<<static_cast<unsigned>((total / 8 + 127) / 128), 128, 0, as_stream(stream)>>>(
+                static_cast<const __nv_bfloat16*>(dpre), w, sigma, dx, B, T, H, W);
+            P2I_CHECK_LAUNCH("d3d_first_bwd_x2_kernel");
+            return P2I_OK;
+        }
         d3d_first_bwd_x_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, as_stream(stream)>>>(
             static_cast<const __nv_bfloat16*>(dpre), w, sigma, dx, B, T, H, W);
         P2I_CHECK_LAUNCH("d3d_first_bwd_x_kernel");

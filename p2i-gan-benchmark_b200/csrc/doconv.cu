@@ -9,13 +9,17 @@
 
 namespace p2i {
 
-// block = (32 input channels) x (8 output-channel lanes); grid = (C/32, C/64, layer)
+// block = 32 input channels x 32 output channels (thread = input channel x 4 output channels); the 9 x 32 x 32 results
+// are staged in shared memory so that BOTH operand layouts are written with contiguous 64-byte warp stores
+// (out: input channels contiguous, out_t: output channels contiguous).  grid = (C/32, C/32, layer)
 __global__ void __launch_bounds__(256) doconv_compose_kernel(const P2iDoLayer* __restrict__ table) {
     const P2iDoLayer L = table[blockIdx.z];
     const int C = L.channels;
-    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     if (i0 >= C || o0 >= C) return;
-    __shared__ float sD[32][82];  // (D + D_diag)[i0 + ii][m*9 + s], padded against bank conflicts
+    __shared__ float sD[32][82];                 // (D + D_diag)[i0 + ii][m*9 + s], padded against bank conflicts
+    __shared__ float sW[8][288];                 // per-warp staging of one output channel's 32 x 9 weights
+    __shared__ __nv_bfloat16 sT[9][32][34];      // [m][o][i], row pitch 17 words: conflict-free both ways
     for (int e = threadIdx.x; e < 32 * 81; e += 256) {
         const int ii = e / 81, r = e - ii * 81;
         const size_t g = static_cast<size_t>(i0 + ii) * 81 + r;
@@ -23,23 +27,31 @@ __global__ void __launch_bounds__(256) doconv_compose_kernel(const P2iDoLayer* _
     }
     __syncthreads();
     const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
-    const int i = i0 + ii;
-    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(L.out);
-    __nv_bfloat16* out_t = static_cast<__nv_bfloat16*>(L.out_t);
-    for (int o = o0 + oo; o < o0 + 64; o += 8) {
-        const float* wp = L.W + (static_cast<size_t>(o) * C + i) * 9;
+    for (int q = 0; q < 4; ++q) {
+        const int ol = oo + 8 * q;
+        const float* wrow = L.W + (static_cast<size_t>(o0 + ol) * C + i0) * 9;      // 288 contiguous floats
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sW[oo][ii + 32 * k] = __ldg(wrow + ii + 32 * k);
+        __syncwarp();
         float w[9];
 #pragma unroll
-        for (int s = 0; s < 9; ++s) w[s] = wp[s];
+        for (int s9 = 0; s9 < 9; ++s9) w[s9] = sW[oo][ii * 9 + s9];
+        __syncwarp();
 #pragma unroll
         for (int m = 0; m < 9; ++m) {
             float acc = 0.f;
 #pragma unroll
-            for (int s = 0; s < 9; ++s) acc = fmaf(sD[ii][m * 9 + s], w[s], acc);
-            const __nv_bfloat16 v = __float2bfloat16(acc);
-            out[(static_cast<size_t>(m) * C + o) * C + i] = v;
-            if (out_t) out_t[(static_cast<size_t>(8 - m) * C + i) * C + o] = v;
+            for (int s9 = 0; s9 < 9; ++s9) acc = fmaf(sD[ii][m * 9 + s9], w[s9], acc);
+            sT[m][ol][ii] = __float2bfloat16(acc);
         }
+    }
+    __syncthreads();
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(L.out);
+    __nv_bfloat16* out_t = static_cast<__nv_bfloat16*>(L.out_t);
+    for (int e = threadIdx.x; e < 9 * 32 * 32; e += 256) {
+        const int lo = e & 31, hi = (e >> 5) & 31, m = e >> 10;
+        out[(static_cast<size_t>(m) * C + o0 + hi) * C + i0 + lo] = sT[m][hi][lo];
+        if (out_t) out_t[(static_cast<size_t>(8 - m) * C + i0 + hi) * C + o0 + lo] = sT[m][lo][hi];
     }
 }
 
@@ -65,7 +77,7 @@ using namespace p2i;
 extern "C" int p2i_doconv_compose_fwd(const P2iDoLayer* table_dev, int n_layers, int max_channels, void* stream) {
     P2I_CHECK_ARG(table_dev && n_layers > 0, "doconv_compose: empty table");
     P2I_CHECK_ARG(max_channels % 64 == 0 && max_channels > 0, "doconv_compose: channels must be a multiple of 64");
-    dim3 grid(max_channels / 32, max_channels / 64, n_layers);
+    dim3 grid(max_channels / 32, max_channels / 32, n_layers);
     doconv_compose_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev);
     P2I_CHECK_LAUNCH("doconv_compose_kernel");
     return P2I_OK;
@@ -86,69 +98,67 @@ extern "C" int p2i_doconv_compose_stem_fwd(const float* W, const float* D, const
 // ------------------------------------------------------------------------------------------------
 namespace p2i {
 
-__global__ void __launch_bounds__(256) doconv_bwd_w_kernel(const P2iDoGrad* __restrict__ table) {
+// One kernel for both gradients.  block = 32 input channels x 64 output channels (thread = input channel x 8 output
+// channels): per output channel the warp loads the 288 contiguous weights and read-modify-writes the 288 contiguous
+// dW values through a per-warp staging buffer (coalesced), keeps the 9x9 dD partial of its input channel in
+// registers, and the block reduces the 8 warps in turn before one global atomic per element.
+__global__ void __launch_bounds__(256) doconv_bwd_kernel(const P2iDoGrad* __restrict__ table) {
     const P2iDoGrad L = table[blockIdx.z];
     const int C = L.channels;
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
     if (i0 >= C || o0 >= C) return;
     __shared__ float sD[32][82];
-    for (int e = threadIdx.x; e < 32 * 81; e += 256) {
-        const int ii = e / 81, r = e - ii * 81;
-        const size_t g = static_cast<size_t>(i0 + ii) * 81 + r;
-        sD[ii][r] = L.D[g] + L.D_diag[g];
-    }
-    __syncthreads();
-    const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
-    const int i = i0 + ii;
-    for (int o = o0 + oo; o < o0 + 64; o += 8) {
-        float g[9];
-#pragma unroll
-        for (int m = 0; m < 9; ++m) g[m] = L.dDoW[(static_cast<size_t>(m) * C + o) * C + i];
-        float* wp = L.dW + (static_cast<size_t>(o) * C + i) * 9;
-#pragma unroll
-        for (int s = 0; s < 9; ++s) {
-            float acc = 0.f;
-#pragma unroll
-            for (int m = 0; m < 9; ++m) acc = fmaf(g[m], sD[ii][m * 9 + s], acc);
-            wp[s] += acc;
-        }
-    }
-}
-
-// block = 32 input channels x 8 output-channel lanes; each thread owns the full 9x9 of its input channel
-// over its share of output channels, then the 8 lanes are reduced through shared memory.
-__global__ void __launch_bounds__(256) doconv_bwd_d_kernel(const P2iDoGrad* __restrict__ table) {
-    const P2iDoGrad L = table[blockIdx.z];
-    const int C = L.channels;
-    const int i0 = blockIdx.x * 32;
-    if (i0 >= C) return;
     __shared__ float red[32][82];
-    for (int e = threadIdx.x; e < 32 * 82; e += 256) (&red[0][0])[e] = 0.f;
+    __shared__ float sW[8][288];
+    for (int e = threadIdx.x; e < 32 * 81; e += 256) {
+        const int a = e / 81, r = e - a * 81;
+        const size_t g = static_cast<size_t>(i0 + a) * 81 + r;
+        sD[a][r] = L.D[g] + L.D_diag[g];
+        red[a][r] = 0.f;
+    }
     __syncthreads();
     const int ii = threadIdx.x & 31, oo = threadIdx.x >> 5;
     const int i = i0 + ii;
     float acc[81];
 #pragma unroll
     for (int k = 0; k < 81; ++k) acc[k] = 0.f;
-    for (int o = oo; o < C; o += 8) {
+    for (int q = 0; q < 8; ++q) {
+        const int o = o0 + oo + 8 * q;
+        const size_t rowoff = (static_cast<size_t>(o) * C + i0) * 9;
         float g[9], w[9];
-        const float* wp = L.W + (static_cast<size_t>(o) * C + i) * 9;
 #pragma unroll
-        for (int m = 0; m < 9; ++m) {
-            g[m] = L.dDoW[(static_cast<size_t>(m) * C + o) * C + i];
-            w[m] = wp[m];
+        for (int m = 0; m < 9; ++m) g[m] = __ldg(L.dDoW + (static_cast<size_t>(m) * C + o) * C + i);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sW[oo][ii + 32 * k] = __ldg(L.W + rowoff + ii + 32 * k);
+        __syncwarp();
+#pragma unroll
+        for (int s9 = 0; s9 < 9; ++s9) w[s9] = sW[oo][ii * 9 + s9];
+        __syncwarp();
+#pragma unroll
+        for (int s9 = 0; s9 < 9; ++s9) {
+            float a = 0.f;
+#pragma unroll
+            for (int m = 0; m < 9; ++m) {
+                a = fmaf(g[m], sD[ii][m * 9 + s9], a);
+                acc[m * 9 + s9] = fmaf(g[m], w[s9], acc[m * 9 + s9]);
+            }
+            sW[oo][ii * 9 + s9] = a;
         }
+        __syncwarp();
 #pragma unroll
-        for (int m = 0; m < 9; ++m)
-#pragma unroll
-            for (int s = 0; s < 9; ++s) acc[m * 9 + s] = fmaf(g[m], w[s], acc[m * 9 + s]);
+        for (int k = 0; k < 9; ++k) L.dW[rowoff + ii + 32 * k] += sW[oo][ii + 32 * k];
+        __syncwarp();
     }
+    for (int wv = 0; wv < 8; ++wv) {
+        if (oo == wv) {
 #pragma unroll
-    for (int k = 0; k < 81; ++k) atomicAdd(&red[ii][k], acc[k]);
-    __syncthreads();
+            for (int k = 0; k < 81; ++k) red[ii][k] += acc[k];
+        }
+        __syncthreads();
+    }
     for (int e = threadIdx.x; e < 32 * 81; e += 256) {
         const int a = e / 81, r = e - a * 81;
-        L.dD[static_cast<size_t>(i0 + a) * 81 + r] += red[a][r];
+        if (red[a][r] != 0.f) atomicAdd(&L.dD[static_cast<size_t>(i0 + a) * 81 + r], red[a][r]);
     }
 }
 
@@ -178,11 +188,8 @@ __global__ void doconv_bwd_stem_kernel(const float* __restrict__ W, const float*
 extern "C" int p2i_doconv_compose_bwd(const P2iDoGrad* table_dev, int n_layers, int max_channels, void* stream) {
     P2I_CHECK_ARG(table_dev && n_layers > 0 && max_channels % 64 == 0, "doconv_compose_bwd: bad table");
     dim3 gw(max_channels / 32, max_channels / 64, n_layers);
-    p2i::doconv_bwd_w_kernel<<<gw, 256, 0, p2i::as_stream(stream)>>>(table_dev);
-    P2I_CHECK_LAUNCH("doconv_bwd_w_kernel");
-    dim3 gd(max_channels / 32, 1, n_layers);
-    p2i::doconv_bwd_d_kernel<<<gd, 256, 0, p2i::as_stream(stream)>>>(table_dev);
-    P2I_CHECK_LAUNCH("doconv_bwd_d_kernel");
+    p2i::doconv_bwd_kernel<<<gw, 256, 0, p2i::as_stream(stream)>>>(table_dev);
+    P2I_CHECK_LAUNCH("doconv_bwd_kernel");
     return P2I_OK;
 }
 

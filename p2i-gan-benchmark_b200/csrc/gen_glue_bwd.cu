@@ -62,11 +62,28 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         dp[0] = o0;
         dp[1] = o1;
     }
+    // reduce over the 8 pixels of the warp (lane bits 2..4), then the 8 warps add into shared memory in turn
+    // (shared-memory float atomics are CAS loops: 64-way contention made this the slowest part of the kernel)
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(&sdw[(g * 4 + o) * 16 + i], acc[o][i]);
-    __syncthreads();
+        for (int i = 0; i < 16; ++i) {
+            float a = acc[o][i];
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            acc[o][i] = a;
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int wv = 0; wv < 8; ++wv) {
+        if (warp == wv && lane < 4) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sdw[(g * 4 + o) * 16 + i] += acc[o][i];
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
 }
 
@@ -295,10 +312,13 @@ __global__ void __launch_bounds__(256) pyramid_bwd_kernel(const __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int H, int W) {
-    __shared__ float sw[64 * 36];
-    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sw[i] = w[i];
-    __syncthreads();
+    __shared__ __align__(16) float sw[9 * 16 * 4];            // this block's group: [tap][oc][ci] -> one LDS.128 per 4 FMAs
     const int b = blockIdx.z >> 2, g = blockIdx.z & 3, yy = blockIdx.y;
+    for (int i = threadIdx.x; i < 9 * 16 * 4; i += blockDim.x) {
+        const int ci = i & 3, oc = (i >> 2) & 15, tap = i >> 6;
+        sw[i] = w[((g * 16 + oc) * 4 + ci) * 9 + tap];
+    }
+    __syncthreads();
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     if (xx >= W) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -313,15 +333,15 @@ __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* _
             const uint4* dp = reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * H + oy) * W + ox) * 64 + g * 16);
             const uint4 u0 = __ldg(dp), u1 = __ldg(dp + 1);
             const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            const float4* wt = reinterpret_cast<const float4*>(sw) + (ky * 3 + kx) * 16;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 f = unpack_bf16x2(uu[i]);
-                const float* w0 = sw + (g * 16 + 2 * i) * 36 + ky * 3 + kx;
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
-                    acc[ci] = fmaf(f.x, w0[ci * 9], acc[ci]);
-                    acc[ci] = fmaf(f.y, w0[36 + ci * 9], acc[ci]);
-                }
+                const float4 wa = wt[2 * i], wb = wt[2 * i + 1];
+                acc[0] = fmaf(f.x, wa.x, fmaf(f.y, wb.x, acc[0]));
+                acc[1] = fmaf(f.x, wa.y, fmaf(f.y, wb.y, acc[1]));
+                acc[2] = fmaf(f.x, wa.z, fmaf(f.y, wb.z, acc[2]));
+                acc[3] = fmaf(f.x, wa.w, fmaf(f.y, wb.w, acc[3]));
                 if (ky == 1 && kx == 1) {   // repeat_interleave: output channel oc feeds input channel oc/4
                     acc[(2 * i) >> 2] += f.x;
                     acc[(2 * i + 1) >> 2] += f.y;
@@ -332,6 +352,60 @@ __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* _
     const size_t HW = static_cast<size_t>(H) * W;
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) dx[(static_cast<size_t>(b) * 16 + g * 4 + ci) * HW + static_cast<size_t>(yy) * W + xx] = acc[ci];
+}
+
+// Weight gradient, tiled: a block stages one image-row segment (64 pixels: the 16 x 3 x 66 input patch and the
+// 64 x 64 gradient tile) in shared memory; thread = (output channel, input channel of its group) with the 9 taps in
+// registers across all of the block's tiles; one global atomic per (block, weight) at the end.
+__global__ void __launch_bounds__(256) stem_bwd_dw2_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                           float* __restrict__ dw, int B, int H, int W) {
+    __shared__ __align__(16) float sx[16][3][68];
+    __shared__ __align__(16) __nv_bfloat16 sdy[64][64];
+    const int oc = threadIdx.x & 63, icl = threadIdx.x >> 6, g = oc >> 4;
+    const int ntx = (W + 63) >> 6;
+    const int ntiles = B * H * ntx;
+    const size_t HW = static_cast<size_t>(H) * W;
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % ntx, r1 = tile / ntx, y = r1 % H, b = r1 / H;
+        const int x0 = tx << 6;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 3 * 66; e += 256) {
+            const int c = e % 66, r2 = e / 66, r = r2 % 3, ch = r2 / 3;
+            const int yi = y + r - 1, xi = x0 + c - 1;
+            sx[ch][r][c] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(x + (static_cast<size_t>(b) * 16 + ch) * HW + static_cast<size_t>(yi) * W + xi) : 0.f;
+        }
+        for (int e = threadIdx.x; e < 64 * 8; e += 256) {
+            const int px = e >> 3, q = e & 7;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (x0 + px < W) v = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * H + y) * W + x0 + px) * 64) + q);
+            *reinterpret_cast<uint4*>(&sdy[px][q * 8]) = v;
+        }
+        __syncthreads();
+        const float* xr = &sx[g * 4 + icl][0][0];
+#pragma unroll 1
+        for (int p0 = 0; p0 < 64; p0 += 8) {
+            float d[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) d[p] = __bfloat162float(sdy[p0 + p][oc]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float4 a = *reinterpret_cast<const float4*>(xr + ky * 68 + p0);
+                const float4 c4 = *reinterpret_cast<const float4*>(xr + ky * 68 + p0 + 4);
+                const float2 e2 = *reinterpret_cast<const float2*>(xr + ky * 68 + p0 + 8);
+                const float v[10] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w, e2.x, e2.y};
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(d[p], v[p + kx], acc[ky * 3 + kx]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        if (acc[k] != 0.f) atomicAdd(&dw[(oc * 4 + icl) * 9 + k], acc[k]);
 }
 
 // thread = (pixel sub-stream s in 0..3, group g, output quad oq, input channel icl): 4 oc x 9 taps accumulators.
@@ -383,7 +457,7 @@ extern "C" int p2i_head_bwd(const float* dout, const float* out, const void* x, 
     P2I_CHECK_ARG(dout && out && x && w && dx && dw, "head_bwd: null pointer");
     const long long npix = static_cast<long long>(B) * H * W;
     long long blocks = (npix + 63) / 64;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     head_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
         dout, out, static_cast<const __nv_bfloat16*>(x), w, static_cast<__nv_bfloat16*>(dx), dw, npix, H * W);
     P2I_CHECK_LAUNCH("head_bwd_kernel");
@@ -426,10 +500,10 @@ extern "C" int p2i_stem_bwd(const void* dy, const float* x, const float* w, floa
     dim3 grid(cdiv(W, 128), H, B * 4);
     stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
     P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");
-    const long long npix = static_cast<long long>(B) * H * W;
-    long long blocks = (npix + 3) / 4;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    stem_bwd_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
-    P2I_CHECK_LAUNCH("stem_bwd_dw_kernel");
+    long long tiles = static_cast<long long>(B) * H * ((W + 63) / 64);
+    P2I_CHECK_ARG(tiles < (1ll << 31), "stem_bwd: tensor too large");
+    if (tiles > sm_count() * 2) tiles = sm_count() * 2;
+    stem_bwd_dw2_kernel<<<static_cast<unsigned>(tiles), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
+    P2I_CHECK_LAUNCH("stem_bwd_dw2_kernel");
     return P2I_OK;
 }

@@ -11,53 +11,68 @@ namespace p2i {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) points_extract_kernel(const float* __restrict__ masks, int Q, int* __restrict__ pts,
                                                                int* __restrict__ counts, int cap) {
+    // warp w owns the contiguous segment [w*seg, (w+1)*seg): pass 1 counts its non-zeros with coalesced 128-element
+    // rounds (no block synchronisation inside the loop), one block scan of the 32 warp totals, pass 2 re-reads the
+    // segment (L1/L2 hits) and writes the ordered indices with ballot prefixes.
     __shared__ int warp_tot[32];
-    __shared__ int base_s, round_tot;
     const int b = blockIdx.x;
     const float* m = masks + static_cast<size_t>(b) * Q;
     int* out = pts + static_cast<size_t>(b) * cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    for (int start = 0; start < Q; start += 4096) {
-        const int i0 = start + threadIdx.x * 4;
-        int flags = 0;
+    const int seg = ((Q + 32 * 128 - 1) / (32 * 128)) * 128;       // multiple of 128 elements
+    const int s0 = warp * seg, s1 = min(Q, s0 + seg);
+    const bool vec = (Q & 3) == 0 && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+    int cnt = 0;
+    for (int i = s0 + lane * 4; i < s1; i += 128) {
+        int f = 0;
+        if (vec) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(m + i));
+            f = (v.x > 0.f) + (v.y > 0.f) + (v.z > 0.f) + (v.w > 0.f);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i0 + j < Q && m[i0 + j] > 0.f) flags |= 1 << j;
-        const int cnt = __popc(flags);
-        int incl = cnt;
+            for (int j = 0; j < 4; ++j) f += (i + j < s1 && m[i + j] > 0.f);
+        }
+        cnt += f;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) warp_tot[warp] = cnt;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    if (threadIdx.x == 0) counts[b] = total < cap ? total : cap;
+    if (cnt == 0) return;                                             // warp-uniform
+    for (int i0 = s0; i0 < s1; i0 += 128) {                           // warp-uniform trip count (shuffles inside)
+        const int i = i0 + lane * 4;
+        int flags = 0;
+        if (i < s1) {
+            if (vec) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(m + i));
+                flags = (v.x > 0.f) | ((v.y > 0.f) << 1) | ((v.z > 0.f) << 2) | ((v.w > 0.f) << 3);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) flags |= (i + j < s1 && m[i + j] > 0.f) << j;
+            }
+        }
+        const int c = __popc(flags);
+        int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int v = warp_tot[lane];
-            int s = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += u;
-            }
-            warp_tot[lane] = s - v;  // exclusive prefix of warp totals
-            if (lane == 31) round_tot = s;
-        }
-        __syncthreads();
-        int pos = base_s + warp_tot[warp] + incl - cnt;
+        int pos = base + incl - c;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (flags & (1 << j)) {
-                if (pos < cap) out[pos] = i0 + j;
+                if (pos < cap) out[pos] = i + j;
                 ++pos;
             }
-        __syncthreads();
-        if (threadIdx.x == 0) base_s += round_tot;
-        __syncthreads();
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x == 0) counts[b] = base_s < cap ? base_s : cap;
 }
 
 // src[b] = 0 when sample b observes exactly the same points as sample 0 (the 'stis' gauge mask is
@@ -96,8 +111,8 @@ __global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const i
     if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
     __syncthreads();
     const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counts[b]) return;
+    const int n = counts[b];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int p = pts[static_cast<size_t>(b) * cap + i];
     const int t = p / HW, pix = p - t * HW;
     const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
@@ -123,6 +138,7 @@ __global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const i
 #pragma unroll
         for (int k = 0; k < 16; ++k) o[k] = h[k];
     }
+    }
 }
 
 // Backward of the two gates for the single output channel t that feeds `vals`.  Per-point contributions are reduced
@@ -146,7 +162,8 @@ __global__ void __launch_bounds__(128) gate_points_bwd_kernel(const float* __res
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {     // block-uniform trip count
+    const int i = base + threadIdx.x;
     const bool active = i < n;
     float x[16], h[16], dg0[16];
     float dg1 = 0.f;
@@ -211,6 +228,7 @@ __global__ void __launch_bounds__(128) gate_points_bwd_kernel(const float* __res
             if (lane == 0 && r != 0.f) atomicAdd(&aw0[j * 16 + k], r);
         }
     }
+    }
     __syncthreads();
     for (int k = threadIdx.x; k < 256; k += blockDim.x) {
         if (aw0[k] != 0.f) atomicAdd(&dw0[k], aw0[k]);
@@ -249,12 +267,22 @@ __device__ __forceinline__ void top4_insert(unsigned long long c, unsigned long 
 
 __global__ void __launch_bounds__(256) idw_search_kernel(const int* __restrict__ pts, const int* __restrict__ counts,
                                                          const int* __restrict__ src, int cap, int* __restrict__ nbr_idx,
-                                                         float* __restrict__ nbr_w, IdwGeom g) {
+                                                         float* __restrict__ nbr_w, IdwGeom g, const int* __restrict__ reuse_flag,
+                                                         int* __restrict__ cache_idx, float* __restrict__ cache_w) {
     __shared__ unsigned s_yx[IDW_SMEM_PTS];
     __shared__ int s_fs[260];
     const int b = blockIdx.y;
     if (src && src[b] != b) return;  // neighbour table shared with sample src[b]
     const int HW = g.H * g.W, Q = g.T * HW;
+    const bool cached = b == 0 && reuse_flag != nullptr;
+    if (cached && *reuse_flag) {     // unchanged point pattern: copy sample 0's rows from the cross-call cache
+        const int q = blockIdx.x * blockDim.x + threadIdx.x;
+        if (q < Q) {
+            reinterpret_cast<int4*>(nbr_idx)[q] = __ldg(reinterpret_cast<const int4*>(cache_idx) + q);
+            reinterpret_cast<float4*>(nbr_w)[q] = __ldg(reinterpret_cast<const float4*>(cache_w) + q);
+        }
+        return;
+    }
     const int N = counts[b];
     const int* P = pts + static_cast<size_t>(b) * cap;
     // frame segment boundaries by binary search: first index with p >= f*HW
@@ -326,6 +354,35 @@ __global__ void __launch_bounds__(256) idw_search_kernel(const int* __restrict__
     const size_t o = (static_cast<size_t>(b) * Q + q) * 4;
     *reinterpret_cast<int4*>(nbr_idx + o) = make_int4(id[0], id[1], id[2], id[3]);
     *reinterpret_cast<float4*>(nbr_w + o) = make_float4(w[0] * norm, w[1] * norm, w[2] * norm, w[3] * norm);
+    if (cached) {
+        reinterpret_cast<int4*>(cache_idx)[q] = make_int4(id[0], id[1], id[2], id[3]);
+        reinterpret_cast<float4*>(cache_w)[q] = make_float4(w[0] * norm, w[1] * norm, w[2] * norm, w[3] * norm);
+    }
+}
+
+// flag = (sample 0's points == cached points); on a mismatch the cache takes the new points.  One block.
+__global__ void __launch_bounds__(1024) idw_cache_check_kernel(const int* __restrict__ pts, const int* __restrict__ counts,
+                                                                int* __restrict__ cache_pts, int* __restrict__ cache_count,
+                                                                int* __restrict__ flag) {
+    __shared__ int differ;
+    if (threadIdx.x == 0) differ = 0;
+    __syncthreads();
+    const int n = counts[0];
+    if (n != *cache_count) {
+        if (threadIdx.x == 0) differ = 1;
+    } else {
+        int d = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d |= (pts[i] != cache_pts[i]);
+        if (d) differ = 1;
+    }
+    __syncthreads();
+    const int df = differ;
+    if (df) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) cache_pts[i] = pts[i];
+        __syncthreads();
+        if (threadIdx.x == 0) *cache_count = n;
+    }
+    if (threadIdx.x == 0) *flag = df ? 0 : 1;
 }
 
 __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* __restrict__ nbr_w,
@@ -346,9 +403,13 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
     out[static_cast<size_t>(b) * Q + q] = r;
 }
 
-// dvals[b, idx] += w * dout.  Each block walks IDW_BWD_SPAN queries of one sample and privatises the scatter in
-// shared memory when the sample has at most IDW_SMEM_PTS points (one global atomic per touched point per block).
-constexpr int IDW_BWD_SPAN = 8192;
+// dvals[b, idx] += w * dout, privatised in shared memory when the sample has at most IDW_SMEM_PTS points (one global
+// atomic per touched point per block).  Shared-memory float atomics are compare-and-swap loops, and neighbouring
+// queries share neighbours, so the lanes of a warp must NOT walk adjacent queries: lane l owns the contiguous run
+// [l*R, (l+1)*R), R = Q/32 (half a frame at 16x128x128), and a block covers IDW_BWD_SPAN offsets of every run.  Lanes
+// then sit in different frames / far-apart rows and hit distinct points; each lane still streams through consecutive
+// addresses, so its 32-byte sectors are reused from L1 on the following iterations.
+constexpr int IDW_BWD_SPAN = 512;
 __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
                                                              const float* __restrict__ nbr_w, const int* __restrict__ counts,
                                                              const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
@@ -362,15 +423,22 @@ __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __rest
     __syncthreads();
     const int sb = src ? src[b] : b;
     float* v = dvals + static_cast<size_t>(b) * cap;
-    const int q0 = blockIdx.x * IDW_BWD_SPAN;
-    const int q1 = min(Q, q0 + IDW_BWD_SPAN);
-    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const float g = dout[static_cast<size_t>(b) * Q + q];
+    float* dst = priv ? acc : v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int R = (Q + 31) >> 5;
+    const int off0 = blockIdx.x * IDW_BWD_SPAN + warp * (IDW_BWD_SPAN / 8);
+    const int4* idp = reinterpret_cast<const int4*>(nbr_idx) + static_cast<size_t>(sb) * Q;
+    const float4* wp = reinterpret_cast<const float4*>(nbr_w) + static_cast<size_t>(sb) * Q;
+    const float* gp = dout + static_cast<size_t>(b) * Q;
+#pragma unroll 4
+    for (int it = 0; it < IDW_BWD_SPAN / 8; ++it) {
+        const int off = off0 + it;
+        const int q = lane * R + off;
+        if (off >= R || q >= Q) continue;
+        const float g = __ldg(gp + q);
         if (g == 0.f) continue;
-        const size_t o = (static_cast<size_t>(sb) * Q + q) * 4;
-        const int4 id = __ldg(reinterpret_cast<const int4*>(nbr_idx + o));
-        const float4 w = __ldg(reinterpret_cast<const float4*>(nbr_w + o));
-        float* dst = priv ? acc : v;
+        const int4 id = __ldg(idp + q);
+        const float4 w = __ldg(wp + q);
         if (w.x != 0.f) atomicAdd(dst + id.x, w.x * g);
         if (w.y != 0.f) atomicAdd(dst + id.y, w.y * g);
         if (w.z != 0.f) atomicAdd(dst + id.z, w.z * g);
@@ -428,7 +496,7 @@ extern "C" int p2i_gate_points_fwd(const float* masked, const int* pts, const in
                                    int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(T == 16, "gate_points: the reference hard-wires 16 frames (layer.py:310), got T=%d", T);
     P2I_CHECK_ARG(masked && pts && counts && w0 && b0 && w1 && b1 && vals, "gate_points: null pointer");
-    dim3 grid(cdiv(cap, 128), B);
+    dim3 grid(cdiv(cap, 128) < 16 ? cdiv(cap, 128) : 16, B);     // blocks stride over the (device-side) point count
     gate_points_fwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(masked, pts, counts, cap, w0, b0, w1, b1, vals, gate_l1,
                                                                 H * W);
     P2I_CHECK_LAUNCH("gate_points_fwd_kernel");
@@ -440,24 +508,34 @@ extern "C" int p2i_gate_points_bwd(const float* masked, const int* pts, const in
                                    float* db0, float* dw1, float* db1, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(T == 16, "gate_points_bwd: T must be 16, got %d", T);
     P2I_CHECK_ARG(masked && pts && counts && dvals && dw0 && db0 && dw1 && db1, "gate_points_bwd: null pointer");
-    dim3 grid(cdiv(cap, 128), B);
+    dim3 grid(cdiv(cap, 128) < 16 ? cdiv(cap, 128) : 16, B);
     gate_points_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(masked, pts, counts, cap, w0, b0, w1, b1, dvals, dw0, db0,
                                                                 dw1, db1, H * W);
     P2I_CHECK_LAUNCH("gate_points_bwd_kernel");
     return P2I_OK;
 }
 
+extern "C" int p2i_idw_cache_check(const int* pts, const int* counts, int cap, int* cache_pts, int* cache_count, int* flag,
+                                   void* stream) {
+    P2I_CHECK_ARG(pts && counts && cache_pts && cache_count && flag && cap > 0, "idw_cache_check: bad arguments");
+    idw_cache_check_kernel<<<1, 1024, 0, as_stream(stream)>>>(pts, counts, cache_pts, cache_count, flag);
+    P2I_CHECK_LAUNCH("idw_cache_check_kernel");
+    return P2I_OK;
+}
+
 extern "C" int p2i_idw_knn_fwd(const int* pts, const float* vals, const int* counts, const int* src, int cap, float* out,
                                int* nbr_idx, float* nbr_w, int B, int T, int H, int W, float tau, int search,
-                               void* stream) {
+                               const int* reuse_flag, int* cache_idx, float* cache_w, void* stream) {
     P2I_CHECK_ARG(pts && vals && counts && out && nbr_idx && nbr_w, "idw_knn_fwd: null pointer");
+    P2I_CHECK_ARG((reuse_flag == nullptr) == (cache_idx == nullptr) && (cache_idx == nullptr) == (cache_w == nullptr),
+                  "idw_knn_fwd: reuse_flag, cache_idx and cache_w go together");
     IdwGeom g;
     int rc = make_geom(T, H, W, tau, &g);
     if (rc) return rc;
     const int Q = T * H * W;
     dim3 grid(cdiv(Q, 256), B);
     if (search) {
-        idw_search_kernel<<<grid, 256, 0, as_stream(stream)>>>(pts, counts, src, cap, nbr_idx, nbr_w, g);
+        idw_search_kernel<<<grid, 256, 0, as_stream(stream)>>>(pts, counts, src, cap, nbr_idx, nbr_w, g, reuse_flag, cache_idx, cache_w);
         P2I_CHECK_LAUNCH("idw_search_kernel");
     }
     idw_interp_kernel<<<grid, 256, 0, as_stream(stream)>>>(nbr_idx, nbr_w, vals, counts, src, cap, out, Q);
@@ -469,7 +547,7 @@ extern "C" int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const floa
                                const int* src, float* dvals, int cap, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dout && nbr_idx && nbr_w && counts && dvals, "idw_knn_bwd: null pointer");
     const int Q = T * H * W;
-    dim3 grid(cdiv(Q, IDW_BWD_SPAN), B);
+    dim3 grid(cdiv((Q + 31) / 32, IDW_BWD_SPAN), B);
     idw_interp_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, nbr_idx, nbr_w, counts, src, cap, dvals, Q);
     P2I_CHECK_LAUNCH("idw_interp_bwd_kernel");
     return P2I_OK;

@@ -186,8 +186,7 @@ class InputBlock(nn.Module):
         if depth != 2 or k != 4 or abs(rho - 2.0) > 1e-6:
             raise ValueError("p2igan_b200.InputBlock implements the P2I-GAN configuration depth=2, k=4, rho=2")
         self.k, self.rho, self.tau, self.chunk = k, rho, tau, chunk
-        self._table = None          # cached neighbour table (valid while the mask is unchanged)
-        self._table_key = None
+        self._cache = None          # ops.IdwTableCache: sample 0's neighbour table across calls (static gauge masks)
 
     def gate_params(self):
         c0, c1 = self.layers[0].conv, self.layers[1].conv
@@ -203,7 +202,11 @@ class InputBlock(nn.Module):
         pts, counts, src = ops.points_extract(mask, cap)
         w0, b0, w1, b1 = (p.detach().contiguous() for p in self.gate_params())
         vals, _ = ops.gate_points_fwd(inp, pts, counts, w0, b0, w1, b1)
-        out, table = ops.idw_knn_fwd(pts, vals, counts, src, (D, H, W), self.tau)
+        key = (D, H, W, float(self.tau), cap, str(inp.device))
+        if self._cache is None or self._cache.key != key:
+            self._cache = ops.IdwTableCache((D, H, W), self.tau, cap, inp.device)
+        self._cache.check(pts, counts)
+        out, table = ops.idw_knn_fwd(pts, vals, counts, src, (D, H, W), self.tau, cache=self._cache)
         ctx = (inp, pts, counts, src, table) if save_for_backward else None
         return out, ctx
 

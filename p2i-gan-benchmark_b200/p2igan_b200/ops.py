@@ -53,8 +53,28 @@ def gate_points_bwd(masked, pts, counts, w0, b0, w1, b1, dvals, dw0, db0, dw1, d
              ptr(_chk(dvals, torch.float32, "dvals")), ptr(dw0), ptr(db0), ptr(dw1), ptr(db1), B, T, H, W, stream())
 
 
-def idw_knn_fwd(pts, vals, counts, src, shape: Tuple[int, int, int], tau: float, table=None):
-    """-> (out [B,T,H,W] f32, (nbr_idx, nbr_w)).  Pass `table` to reuse a neighbour table (no search)."""
+class IdwTableCache:
+    """Device-resident copy of sample 0's neighbour table, reused while its point pattern is unchanged (decided on
+    the device by p2i_idw_cache_check: no host synchronisation, CUDA-graph capturable)."""
+
+    def __init__(self, shape: Tuple[int, int, int], tau: float, cap: int, device):
+        T, H, W = shape
+        self.key = (T, H, W, float(tau), cap, str(device))
+        self.pts = torch.zeros(cap, dtype=torch.int32, device=device)
+        self.count = torch.full((1,), -1, dtype=torch.int32, device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.idx = torch.zeros(T * H * W, 4, dtype=torch.int32, device=device)
+        self.w = torch.zeros(T * H * W, 4, dtype=torch.float32, device=device)
+
+    def check(self, pts: Tensor, counts: Tensor):
+        LIB.call("p2i_idw_cache_check", ptr(pts), ptr(counts), pts.shape[1], ptr(self.pts), ptr(self.count), ptr(self.flag),
+                 stream())
+
+
+def idw_knn_fwd(pts, vals, counts, src, shape: Tuple[int, int, int], tau: float, table=None,
+                cache: Optional[IdwTableCache] = None):
+    """-> (out [B,T,H,W] f32, (nbr_idx, nbr_w)).  Pass `table` to reuse a neighbour table (no search); pass `cache`
+    (after cache.check) to let sample 0's rows come from / go to the cross-call cache."""
     T, H, W = shape
     B, cap = pts.shape
     Q = T * H * W
@@ -64,7 +84,8 @@ def idw_knn_fwd(pts, vals, counts, src, shape: Tuple[int, int, int], tau: float,
         table = (torch.empty(B, Q, 4, dtype=torch.int32, device=pts.device),
                  torch.empty(B, Q, 4, dtype=torch.float32, device=pts.device))
     LIB.call("p2i_idw_knn_fwd", ptr(pts), ptr(vals), ptr(counts), ptr(src), cap, ptr(out), ptr(table[0]), ptr(table[1]),
-             B, T, H, W, float(tau), 1 if search else 0, stream())
+             B, T, H, W, float(tau), 1 if search else 0, ptr(cache.flag if cache else None),
+             ptr(cache.idx if cache else None), ptr(cache.w if cache else None), stream())
     return out, table
 
 

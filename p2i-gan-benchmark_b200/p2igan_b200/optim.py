@@ -15,21 +15,31 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
+        self._stepbufs = {}
 
-    def _init_state(self, group):
+    def _init_state(self, gi, group):
         plist = [p for p in group["params"] if p.requires_grad or p.grad is not None]
         dev = plist[0].device
-        step = None
+        # one device buffer per group: [step, lr/(1-b1^t), 1/sqrt(1-b2^t), pad]; every state["step"] is a 0-dim view of [0]
+        buf = self._stepbufs.get(gi)
+        if buf is None or buf.device != dev:
+            buf = torch.zeros(4, dtype=torch.float32, device=dev)
+            self._stepbufs[gi] = buf
+            seeded = False
+        else:
+            seeded = True
+        step = buf[0]
         for p in plist:
             st = self.state[p]
             if "exp_avg" not in st:
-                if step is None:
-                    step = torch.zeros((), dtype=torch.float32, device=dev)
-                st["step"] = step                     # one shared device counter per group
+                st["step"] = step
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            elif not st["step"].is_cuda:              # state loaded from a torch.optim.Adam checkpoint
-                st["step"] = st["step"].to(dev, torch.float32)
+            elif st["step"].data_ptr() != step.data_ptr():     # state loaded from a (torch.optim.Adam) checkpoint
+                if not seeded:
+                    buf[0] = st["step"].to(dev, torch.float32)
+                    seeded = True
+                st["step"] = step
 
     def _table(self, gi, plist):
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
@@ -56,7 +66,7 @@ class FusedAdam(torch.optim.Optimizer):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
                 continue
-            self._init_state(group)
+            self._init_state(gi, group)
             for p in plist:
                 if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
                     raise RuntimeError("FusedAdam needs contiguous float32 parameters and gradients")
