@@ -252,7 +252,7 @@ def run_ours(args):
     import torch.distributed as dist
     from p2igan_b200 import build_discriminator, build_generator
     from p2igan_b200._lib import LIB
-    from p2igan_b200.train_step import GANTrainStep, GraphedStep
+    from p2igan_b200.train_step import GANTrainStep, GraphedDPStep, GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,23 +291,62 @@ def run_ours(args):
         with torch.no_grad():
             return G(mf, mk)
 
-    # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch
-    # (multi-GPU runs launch eagerly: the NCCL all-reduces sit between kernels of the step and are not captured)
-    graphed = None if (args.no_graph or (world > 1 and train)) else GraphedStep(eager, batches[0], warmup=3)
+    LOSS_KEYS = ("rec", "pool", "reg", "adv", "dis", "total")
+    # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch.  Multi-GPU
+    # training replays three graphs with the two NCCL all-reduces between them (GraphedDPStep).
+    graphed = None
+    if not args.no_graph:
+        if world > 1 and train:
+            dp = GraphedDPStep(ts, batches[0], warmup=3)
+
+            class _DP:
+                static_in = dp.static_in
+
+                def __call__(self, *inp):
+                    o = dp(*inp)
+                    return torch.stack([o[k] for k in LOSS_KEYS])
+            graphed = _DP()
+        else:
+            graphed = GraphedStep(eager, batches[0], warmup=3)
     run = graphed if graphed is not None else eager
 
     def step(i):
         return run(*batches[i % 4])
 
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, software-pipelined over three streams
+    # (H2D of step i+1 and D2H of step i-1 overlap the compute of step i; every copy is inside the timed region)
+    main = torch.cuda.current_stream()
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    stage_in = [tuple(torch.empty_like(t) for t in batches[0]) for _ in range(2)]
+    res_shape = (6,) if train else (B, T, 1, H, W)
+    stage_out = [torch.empty(res_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    ev_in_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_in_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_out_free = [torch.cuda.Event() for _ in range(2)]
+    res_host = loss_host if train else out_host
+
     def e2e_step(i):
-        fr, mf, mk = host[i % 2]
-        if graphed is not None:          # H2D straight into the graph's static input buffers
-            for s_, t_ in zip(graphed.static_in, (fr, mf, mk)):
-                s_.copy_(t_, non_blocking=True)
-            o = graphed(*graphed.static_in)
-        else:
-            o = eager(fr.to(dev, non_blocking=True), mf.to(dev, non_blocking=True), mk.to(dev, non_blocking=True))
-        (loss_host if train else out_host).copy_(o, non_blocking=True)
+        k = i % 2
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_in_free[k])
+            for j in ((0, 1, 2) if train else (1, 2)):       # inference reads masked_frames and masks only
+                stage_in[k][j].copy_(host[k][j], non_blocking=True)
+            ev_in_ready[k].record(s_h2d)
+        main.wait_event(ev_in_ready[k])
+        o = run(*stage_in[k])                       # graphed: one D2D copy into the static inputs + replay
+        ev_in_free[k].record(main)
+        main.wait_event(ev_out_free[k])
+        stage_out[k].copy_(o.reshape(res_shape), non_blocking=True)
+        ev_out_ready[k].record(main)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_out_ready[k])
+            res_host.copy_(stage_out[k], non_blocking=True)
+            ev_out_free[k].record(s_d2h)
+
+    def e2e_drain():
+        main.wait_stream(s_d2h)
+        main.wait_stream(s_h2d)
 
     for i in range(max(3, args.warmup)):
         step(i)
@@ -336,11 +375,13 @@ def run_ours(args):
 
     for i in range(2):
         e2e_step(i)
+    e2e_drain()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
         e2e_step(i)
+    e2e_drain()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -375,7 +416,9 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS,
-                       "weights": "random init seed 2024", "launch": "eager" if graphed is None else "CUDA graph replay",
+                       "weights": "random init seed 2024",
+                       "launch": "eager" if graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train) else "CUDA graph replay"),
+                       "e2e_pipeline": "H2D / step / D2H on three streams, double-buffered",
                        "parallelism": (f"data parallel over {world} GPU(s): flat NCCL all-reduce of D and G gradients" if train
                                        else f"events sharded over {world} GPU(s), no collective"),
                        "l2": "no explicit flush: 4 rotating input batches and a per-step activation working set of several GB, "

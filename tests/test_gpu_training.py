@@ -242,3 +242,46 @@ def test_gan_train_step_matches_oracle_and_reference_golden(golden):
     for k in d_sd:
         if k.endswith("_u") or k.endswith("_v"):
             assert float((gotd[k] - d_sd[k]).abs().max()) < 1e-3, k
+
+
+def test_three_graph_dp_step_equals_eager_step():
+    """GraphedDPStep (seg_a | all-reduce D | seg_b | all-reduce G | seg_c as three CUDA graphs, world size 1) must
+    reproduce the eager step: same losses and same parameters after 3 iterations (wgrad atomics make the two runs
+    differ at fp32 summation-order level only; Adam with beta1 = 0 can flip lr-sized steps of noise-floor elements)."""
+    from p2igan_b200 import build_discriminator, build_generator
+    from p2igan_b200.train_step import GANTrainStep, GraphedDPStep
+    cfg = synth.make_cfg(32, 32)
+    batches = [tuple(t.to(DEV) for t in synth.make_batch(2, 16, 32, 32, 12, 200 + i)) for i in range(3)]
+
+    def run(graphed):
+        torch.manual_seed(2024)
+        G, D = build_generator(cfg).to(DEV).train(), build_discriminator(cfg).to(DEV).train()
+        ts = GANTrainStep(cfg, G, D)
+        losses = []
+        if graphed:
+            g0 = {k: v.detach().clone() for k, v in G.state_dict().items()}
+            d0 = {k: v.detach().clone() for k, v in D.state_dict().items()}
+            dp = GraphedDPStep(ts, batches[0], warmup=2)        # warm-up + capture advance the model: restore it
+            G.load_state_dict(g0); D.load_state_dict(d0)
+            for opt in (ts.opt_g, ts.opt_d):
+                for st in opt.state.values():
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                for buf in opt._stepbufs.values():
+                    buf.zero_()
+            for b in batches:
+                losses.append({k: float(v) for k, v in dp(*b).items()})
+        else:
+            for b in batches:
+                losses.append({k: float(v) for k, v in ts.step(*b).items()})
+        return losses, {k: v.detach().clone() for k, v in G.state_dict().items()}
+
+    le, ge = run(False)
+    lg, gg = run(True)
+    for it, (a, b) in enumerate(zip(le, lg)):
+        # iteration 0 starts from identical parameters: only the atomics' summation order differs.  Later iterations
+        # inherit lr-sized sign flips of noise-floor elements (Adam, beta1 = 0), hence the looser bound.
+        tol = 2e-4 if it == 0 else 1e-2
+        for k in a:
+            assert abs(a[k] - b[k]) < tol * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
+    for k in ge:
+        assert float((ge[k] - gg[k]).abs().max()) <= 7e-4, k
