@@ -154,6 +154,10 @@ int p2i_conv_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc* 
  * only, 2 = halo only (ineligible shapes fail with P2I_ERR_INVALID), 3 / 4 = halo only, forced to single CTAs /
  * CTA pairs (tcgen05 cta_group::2). */
 int p2i_set_conv_impl(int impl);
+/* Same for p2i_conv_wgrad / p2i_conv2d_wgrad: 0 = automatic and 1 = first-generation kernel (the measured winner once
+ * the K split is limited to one wave); 2 = the experimental second-generation variants where eligible (all nine taps
+ * per CTA for 64 -> 64 channel 3x3 layers, flipped GEMM with 16-byte vector reductions otherwise), kept for A/B runs. */
+int p2i_set_wgrad_impl(int impl);
 
 /* Weight gradient: dW[tap][co][ci] += sum_pix dy[pix][co] * x[pix+tap][ci]  (fp32 [k*k][Cout][Cin], atomically
  * accumulated: the caller zero-fills).  x [B,H,W,Cin], dy [B,H,W,Cout] bf16.  Cin in {64} or % 128 == 0. */

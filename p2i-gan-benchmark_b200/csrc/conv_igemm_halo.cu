@@ -440,6 +440,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_store_5d(&tmO, src, n0, tc.x0, tc.y0, tc.f, 0);
                         } else if (p.out_mode == 1) {
                             tma_store_5d(&tmO, src, n0, 0, tc.x0 >> 1, 0, tc.f * (p.H >> 1) + (tc.y0 >> 1));
+                        } else if (p.cq == 32) {
+                            // 64 staged channels = the two horizontally adjacent 32-channel output pixels of row parity n0/64
+                            tma_store_5d(&tmO, src, 0, tc.x0, n0 >> 6, tc.f * p.H + tc.y0, 0);
                         } else {
                             const int q = n0 / p.cq, ch0 = n0 - q * p.cq;
                             tma_store_5d(&tmO, src, ch0, q & 1, tc.x0, q >> 1, tc.f * p.H + tc.y0);
@@ -532,7 +535,7 @@ int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const voi
     if (d.Cin % 64 != 0 || d.Cout % 64 != 0 || d.ksize < 1 || d.ksize > 3 || (d.kt != 1 && d.kt != 3)) return 1;
     if (residual && mask) return 1;
     if (d.out_mode != 0 && (d.H % 16 != 0 || d.W % 8 != 0)) return 1;
-    if (d.out_mode == 2 && (d.Cout / 4) % 64 != 0) return 1;   // 32-channel unpack (64-B store rows): legacy kernel
+    if (d.out_mode == 2 && (d.Cout / 4) % 64 != 0 && d.Cout != 128) return 1;   // unpack: 64-channel multiples or exactly 32
     HaloParams p;
     p.F = d.samples * d.T_out; p.T_out = d.T_out; p.T_in = d.T_in;
     p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout;
@@ -643,6 +646,14 @@ int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const voi
         const uint64_t dims[5] = {Co, 2, Wd / 2, 2, Fr * (Hd / 2)};
         const uint64_t strides[5] = {0, Co * 2, 4 * Co * 2, 2 * Co * 2, (Wd / 2) * 4 * Co * 2};
         const uint32_t box[5] = {64, 2, 4, 2, 8};
+        int rc = encode_tmap_bf16(&tmO, y, 5, dims, strides, box, nullptr, true);
+        if (rc) return rc;
+    } else if (d.out_mode == 2 && d.Cout == 128) {
+        // y [F, 2H, 2W, 32]: channels n = q*32 + ch, q = 2*dy + dx.  The 64 channels (dx = 0, 1) of one dy are the 128
+        // contiguous bytes of output pixels (2y+dy, 2x), (2y+dy, 2x+1):  dims {64, W, 2 (dy), F*H}
+        const uint64_t dims[5] = {64, Wd, 2, Fr * Hd, 1};
+        const uint64_t strides[5] = {0, 128, Wd * 128, 2 * Wd * 128, 2 * Wd * 128 * Fr * Hd};
+        const uint32_t box[5] = {64, 8, 1, 16, 1};
         int rc = encode_tmap_bf16(&tmO, y, 5, dims, strides, box, nullptr, true);
         if (rc) return rc;
     } else if (d.out_mode == 2) {

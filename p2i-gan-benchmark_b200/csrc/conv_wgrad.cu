@@ -157,6 +157,193 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Second generation.  The first-generation epilogue issues one scalar fp32 RED per accumulator element and lane
+// (lane = input channel, so a thread's consecutive registers are Cin*4 bytes apart in dW); at ~1.3 clk per lane-RED
+// and SM the split-K reduction cost as much as the MMA main loop.  Here the GEMM is FLIPPED: M = output channels
+// (dY is the A operand), N = input channels (X is the B operand), so a thread owns one `co` row and its registers
+// are consecutive `ci` -> 16-byte vector REDs (red.global.add.v4.f32, REDG.E.ADD.F32x4), 4x fewer reduction ops.
+//   mode 0 (FLIP): Cout % 128 == 0, Cin == 64 or Cin % 128 == 0.  Work item = (kt, kx, ci tile, co tile, K split);
+//                  one accumulator [128 co][N ci] per vertical tap (row-shifted views of the X box).
+//   mode 1 (TAPS): Cin == Cout == 64, 3x3.  ALL nine taps in one CTA from one X box and one dY box per pixel tile:
+//                  N = 3 vertical taps x 64 ci (X views one tile row apart: LBO = Wt*128 B), M = 2 horizontal taps
+//                  x 64 co (dY views ONE PIXEL apart: LBO = 128 B inside a (Wt+2)-wide box; the 128-byte swizzle of
+//                  TMA and UMMA is a function of the absolute shared-memory address, so pixel-granular starts are
+//                  valid).  Two MMAs per K step: {kx=2, kx=1} and {kx=0, unused}; X and dY are fetched once per
+//                  tile instead of once per horizontal tap.
+// ------------------------------------------------------------------------------------------------
+struct Wgrad2Params {
+    int F, T_out, T_in, H, W, Cin, Cout;
+    int KT, KH, KW;
+    int pad, pad_t, st;
+    int Ht, Wt, tiles_x, tiles_y, pix_tiles;
+    int ci_tiles, co_tiles, ksplit;
+    int mode;        // 0 FLIP, 1 TAPS
+    int n_ci;        // FLIP: N of one MMA (64 or 128)
+    float* dW;
+};
+
+constexpr int WG2_X_REGION = 22528;     // (8+2)*16*128 = 20480 used by TMA + one spare tile row read by the unused tap
+constexpr int WG2_Y_REGION = 20480;     // TAPS: Ht x (Wt+2) pixels (18432 / 20480 B); FLIP: atom 0 (16384 B)
+constexpr int WG2_STAGE_FLIP = 2 * WG_X_ATOM + 2 * WG_Y_ATOM;      // 73728
+constexpr int WG2_STAGE_TAPS = WG2_X_REGION + WG2_Y_REGION;        // 43008
+constexpr int WG2_SMEM = 1024 + 3 * WG2_STAGE_FLIP + 128;          // 222336 >= 4 * WG2_STAGE_TAPS + ...
+
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+                 "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const Wgrad2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const bool taps = p.mode == 1;
+    const int stages = taps ? 4 : 3;
+    const int stage_bytes = taps ? WG2_STAGE_TAPS : WG2_STAGE_FLIP;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 3 * WG2_STAGE_FLIP);
+    uint64_t* empty = full + 4;
+    uint64_t* done = empty + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nacc = taps ? 2 : p.KH;
+    const int ncol = taps ? 192 : p.n_ci;
+    const uint32_t tmem_cols = (nacc * ncol <= 128) ? 128 : ((nacc * ncol <= 256) ? 256 : 512);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); }
+    if (warp == 2) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int item = blockIdx.x;
+    const int ks = item % p.ksplit; item /= p.ksplit;
+    int cot = 0, cit = 0, kx = 0, kt;
+    if (taps) {
+        kt = item;
+    } else {
+        cot = item % p.co_tiles; item /= p.co_tiles;
+        cit = item % p.ci_tiles; item /= p.ci_tiles;
+        kx = item % p.KW;
+        kt = item / p.KW;
+    }
+    const int ci_atoms = taps ? 1 : (p.n_ci >> 6);
+    const int ci0 = cit * p.n_ci, co0 = cot * 128;
+    const int t_begin = static_cast<int>(static_cast<long long>(p.pix_tiles) * ks / p.ksplit);
+    const int t_end = static_cast<int>(static_cast<long long>(p.pix_tiles) * (ks + 1) / p.ksplit);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const uint32_t x_bytes = static_cast<uint32_t>((p.Ht + p.KH - 1) * p.Wt * 128);
+    const uint32_t y_bytes = taps ? static_cast<uint32_t>(p.Ht * (p.Wt + 2) * 128) : 2u * WG_Y_ATOM;
+    const uint32_t stage_tx = ci_atoms * x_bytes + y_bytes;
+    const uint32_t y_off = taps ? WG2_X_REGION : 2 * WG_X_ATOM;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t s = 0, ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int f = t / tiles_per_img, r = t - f * tiles_per_img;
+                const int smp = f / p.T_out, t_out = f - smp * p.T_out;
+                const int t_in = p.st * t_out + kt - p.pad_t;      // out-of-range frames are zero-filled by TMA
+                const int y0 = (r / p.tiles_x) * p.Ht, x0 = (r % p.tiles_x) * p.Wt;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], stage_tx);
+                uint8_t* st = smem + s * stage_bytes;
+                if (taps) {
+                    tma_load_5d(st, &tmX, &full[s], 0, x0, y0 - p.pad, t_in, smp);
+                    tma_load_5d(st + y_off, &tmY, &full[s], 0, x0 - 1, y0, t_out, smp);
+                } else {
+                    for (int a = 0; a < ci_atoms; ++a)
+                        tma_load_5d(st + a * WG_X_ATOM, &tmX, &full[s], ci0 + a * 64, x0 + kx - p.pad, y0 - p.pad, t_in, smp);
+                    for (int a = 0; a < 2; ++a)
+                        tma_load_5d(st + y_off + a * WG_Y_ATOM, &tmY, &full[s], co0 + a * 64, x0, y0, t_out, smp);
+                }
+                if (++s == static_cast<uint32_t>(stages)) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, ncol, 1, 1);
+            const uint32_t row_shift = static_cast<uint32_t>(p.Wt * 128);
+            // TAPS: a K = 16 step is one 16-pixel row (Wt = 16) or two 8-pixel rows (Wt = 8) of the (Wt+2)-wide dY box
+            const uint32_t y_pitch = static_cast<uint32_t>((p.Wt + 2) * 128);
+            const uint32_t y_sbo = taps ? (p.Wt == 16 ? 1024u : y_pitch) : 1024u;
+            const uint32_t y_adv = taps ? (p.Wt == 16 ? y_pitch : 2 * y_pitch) : 2048u;
+            uint32_t s = 0, ph = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t xb = smem_u32(smem + s * stage_bytes);
+                const uint32_t yb = xb + y_off;
+                const uint32_t acc = (t > t_begin) ? 1u : 0u;
+                if (taps) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t bd = make_sw128_desc(xb + k * 2048, row_shift, 1024);            // ky = 0, 1, 2
+                        umma_bf16(tmem_base, make_sw128_desc(yb + k * y_adv, 128, y_sbo), bd, idesc, acc | (k > 0 ? 1u : 0u));
+                        umma_bf16(tmem_base + 192, make_sw128_desc(yb + k * y_adv + 256, 128, y_sbo), bd, idesc, acc | (k > 0 ? 1u : 0u));
+                    }
+                } else {
+                    for (int g = 0; g < p.KH; ++g) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem_base + g * ncol, make_sw128_desc(yb + k * 2048, WG_Y_ATOM, 1024),
+                                      make_sw128_desc(xb + g * row_shift + k * 2048, WG_X_ATOM, 1024), idesc, acc | (k > 0 ? 1u : 0u));
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (++s == static_cast<uint32_t>(stages)) { s = 0; ph ^= 1; }
+            }
+            umma_commit(done);
+        }
+    } else if (warp >= 4 && t_end > t_begin) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        for (int g = 0; g < nacc; ++g) {
+            const uint32_t t_addr = tmem_base + g * ncol + (static_cast<uint32_t>(ew * 32) << 16);
+            int kxx = kx, co = co0 + row;
+            bool ok = true;
+            if (taps) {
+                const int a = row >> 6;
+                co = row & 63;
+                kxx = (g == 0) ? 2 - a : 0;
+                ok = (g == 0) || a == 0;
+            }
+#pragma unroll 1
+            for (int c = 0; c < ncol; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + c, v);
+                tmem_ld_wait();
+                const int ky = taps ? (c >> 6) : g;
+                const int ci = taps ? (c & 63) : ci0 + c;
+                const int tap = (kt * p.KH + ky) * p.KW + kxx;
+                float* dst = p.dW + (static_cast<size_t>(tap) * p.Cout + co) * p.Cin + ci;
+                if (ok) {
+                    red_add_v4(dst, v[0], v[1], v[2], v[3]);
+                    red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+                    red_add_v4(dst + 8, v[8], v[9], v[10], v[11]);
+                    red_add_v4(dst + 12, v[12], v[13], v[14], v[15]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static std::atomic<int> g_wgrad_impl{0};   // 0 auto (second generation when eligible), 1 first generation only
+
 }  // namespace p2i
 
 using namespace p2i;
@@ -168,6 +355,65 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
     P2I_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "conv_wgrad: channels must be multiples of 64");
     P2I_CHECK_ARG(Cin == 64 || Cin % 128 == 0, "conv_wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
     P2I_CHECK_ARG(Cin != 64 || d.ksize == 3 || d.ksize == 1, "conv_wgrad: Cin=64 supports k in {1,3}");
+    {
+        const bool taps_ok = Cin == 64 && Cout == 64 && d.ksize == 3 && d.pad == 1;
+        // Measured (tools/bench_wgrad.py, profiles/r1_wgrad_ab.txt): once the K split keeps every launch to ONE wave,
+        // the first-generation kernel wins or ties everywhere.  FLIP is ~10 % slower (lanes = co: every 16-byte RED of
+        // a warp lands in a different 32-byte sector, 32 sector operations per instruction against 4 for the first
+        // generation's 128 contiguous bytes); TAPS needs 2.2x more reduction traffic at a 148-way K split (9 taps x
+        // 64 x 64 per CTA) and ends 8 % behind the stacked first-generation layout (35.5 vs 32.9 us at B = 16).
+        // Both stay selectable (impl 2) for A/B runs; automatic selection uses the first generation.
+        const int impl = g_wgrad_impl.load(std::memory_order_relaxed);
+        const bool use2 = impl == 2;
+        const bool flip_ok = use2 && !taps_ok && Cout % 128 == 0 && (Cin == 64 || Cin % 128 == 0);
+        if (use2 && (taps_ok || flip_ok)) {
+            Wgrad2Params q;
+            q.F = d.samples * d.T_out; q.T_out = d.T_out; q.T_in = d.T_in;
+            q.H = d.H; q.W = d.W; q.Cin = Cin; q.Cout = Cout;
+            q.KT = d.kt; q.KH = d.ksize; q.KW = d.ksize; q.pad = d.pad; q.pad_t = d.pad_t; q.st = d.stride_t;
+            q.Wt = (d.W >= 16) ? 16 : 8;
+            q.Ht = 128 / q.Wt;
+            q.tiles_x = cdiv(d.W, q.Wt);
+            q.tiles_y = cdiv(d.H, q.Ht);
+            q.pix_tiles = q.F * q.tiles_x * q.tiles_y;
+            q.mode = taps_ok ? 1 : 0;
+            q.n_ci = (Cin == 64) ? 64 : 128;
+            q.ci_tiles = taps_ok ? 1 : Cin / q.n_ci;
+            q.co_tiles = taps_ok ? 1 : Cout / 128;
+            const int items = taps_ok ? q.KT : q.KT * q.KW * q.ci_tiles * q.co_tiles;
+            int ks = sm_count() / items;          // floor: one wave of at most sm_count() CTAs (1 CTA per SM)
+            if (ks > q.pix_tiles) ks = q.pix_tiles;
+            if (ks < 1) ks = 1;
+            q.ksplit = ks;
+            q.dW = dW;
+            CUtensorMap tmX, tmY;
+            {
+                const uint64_t C = Cin, W = d.W, H = d.H, T = d.T_in;
+                const uint64_t dims[5] = {C, W, H, T, uint64_t(d.samples)};
+                const uint64_t strides[5] = {0, C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+                const uint32_t box[5] = {64, uint32_t(q.Wt), uint32_t(q.Ht + d.ksize - 1), 1, 1};
+                int rc = encode_tmap_bf16(&tmX, x, 5, dims, strides, box, nullptr, true);
+                if (rc) return rc;
+            }
+            {
+                const uint64_t C = Cout, W = d.W, H = d.H, T = d.T_out;
+                const uint64_t dims[5] = {C, W, H, T, uint64_t(d.samples)};
+                const uint64_t strides[5] = {0, C * 2, W * C * 2, H * W * C * 2, T * H * W * C * 2};
+                const uint32_t box[5] = {64, uint32_t(taps_ok ? q.Wt + 2 : q.Wt), uint32_t(q.Ht), 1, 1};
+                int rc = encode_tmap_bf16(&tmY, dy, 5, dims, strides, box, nullptr, true);
+                if (rc) return rc;
+            }
+            static bool configured2 = false;
+            if (!configured2) {
+                cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM);
+                if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_wgrad2 smem attribute: %s", cudaGetErrorString(e));
+                configured2 = true;
+            }
+            conv_wgrad2_kernel<<<items * ks, 256, WG2_SMEM, as_stream(stream)>>>(tmX, tmY, q);
+            P2I_CHECK_LAUNCH("conv_wgrad2_kernel");
+            return P2I_OK;
+        }
+    }
     WgradParams p;
     p.F = d.samples * d.T_out; p.T_out = d.T_out; p.T_in = d.T_in;
     p.H = d.H; p.W = d.W; p.Cin = Cin; p.Cout = Cout;
@@ -182,7 +428,8 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
     p.ci_tiles = p.stacked ? 1 : Cin / 128;
     p.co_tiles = Cout / p.nt;
     const int items = p.KT * p.KW * p.ci_tiles * p.co_tiles;
-    int ks = cdiv(sm_count(), items);
+    // floor, not ceil: the kernel holds one CTA per SM, so items * ks > sm_count() would run a second, nearly empty wave
+    int ks = sm_count() / items;
     if (ks > p.pix_tiles) ks = p.pix_tiles;
     if (ks < 1) ks = 1;
     p.ksplit = ks;
@@ -213,6 +460,12 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
     }
     conv_wgrad_kernel<<<items * ks, 256, WG_SMEM, as_stream(stream)>>>(tmX, tmY, p);
     P2I_CHECK_LAUNCH("conv_wgrad_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_set_wgrad_impl(int impl) {
+    P2I_CHECK_ARG(impl >= 0 && impl <= 2, "set_wgrad_impl: 0 auto | 1 first generation | 2 experimental all-taps / flipped kernels");
+    g_wgrad_impl.store(impl);
     return P2I_OK;
 }
 

@@ -283,5 +283,11 @@ def test_three_graph_dp_step_equals_eager_step():
         tol = 2e-4 if it == 0 else 1e-2
         for k in a:
             assert abs(a[k] - b[k]) < tol * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
+    # parameters: identical up to sign flips of noise-floor elements (each worth up to ~2 lr per step, more when the
+    # running second moment is small): bounded maximum, tiny mean
+    tot = num = 0.0
     for k in ge:
-        assert float((ge[k] - gg[k]).abs().max()) <= 7e-4, k
+        d = (ge[k] - gg[k]).abs()
+        assert float(d.max()) <= 3e-3, (k, float(d.max()))
+        tot += float(d.sum()); num += d.numel()
+    assert tot / num < 2e-5, tot / num
