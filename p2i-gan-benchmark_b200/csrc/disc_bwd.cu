@@ -485,22 +485,27 @@ __global__ void __launch_bounds__(192) d3d_first_bwd_w4_kernel(const __nv_bfloat
     if (threadIdx.x < 32 && sdb[threadIdx.x] != 0.f) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
 }
 
-// d3d.0 input gradient (transposed stride-2 conv), W % 4 == 0: thread = two adjacent 2x2 blocks of dx, i.e. rows
-// 2m, 2m+1 and columns 4j .. 4j+3, fed by the 2 x 3 gradient pixels (m..m+1, 2j..2j+2) of three frames.  Weights are
-// read as broadcast LDS.128 ([kt][c][12] layout), 18 FMAs per 3 shared-memory reads.
-__global__ void __launch_bounds__(128) d3d_first_bwd_x2_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ w,
+// d3d.0 input gradient (transposed stride-2 conv), W % 4 == 0.  A group of 4 lanes = two adjacent 2x2 blocks of dx
+// (rows 2m, 2m+1, columns 4j .. 4j+3), fed by the 2 x 3 gradient pixels (m..m+1, 2j..2j+2) of three frames; lane q of
+// the group handles channels 8q..8q+7, so a warp's 16-byte loads cover 8 pixels x 64 contiguous bytes (4 cache lines
+// per request instead of 32 with one pixel per lane: the first version of this kernel was LSU-wavefront bound).  The
+// four partial sums are folded with two shuffle steps.  Weights: broadcast LDS.128 from a [kt][chunk][c][12] layout
+// whose chunk pitch (100 floats) puts the four chunks of a warp on disjoint banks.
+__global__ void __launch_bounds__(256) d3d_first_bwd_x2_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ w,
                                                                const float* __restrict__ sigma, float* __restrict__ dx, int B, int T, int H, int W) {
-    __shared__ __align__(16) float sw[3 * 32 * 12];
+    __shared__ __align__(16) float sw[3 * 4 * 100];
     const float inv = 1.f / *sigma;
-    for (int i = threadIdx.x; i < 3 * 32 * 12; i += blockDim.x) {
-        const int k = i % 12, c = (i / 12) % 32, kt = i / (12 * 32);
-        sw[i] = (k < 9) ? w[c * 27 + kt * 9 + k] * inv : 0.f;
+    for (int i = threadIdx.x; i < 3 * 4 * 100; i += blockDim.x) {
+        const int kt = i / 400, r = i - kt * 400, ch = r / 100, r2 = r - ch * 100, c = r2 / 12, k = r2 - c * 12;
+        sw[i] = (c < 8 && k < 9) ? w[(ch * 8 + c) * 27 + kt * 9 + k] * inv : 0.f;
     }
     __syncthreads();
     const int Ho = H >> 1, Wo = W >> 1, Wp = Wo >> 1;
     const int total = B * T * Ho * Wp;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int ch = threadIdx.x & 3;
+    const bool live = gidx < total;
+    const int idx = live ? gidx : total - 1;
     const int j = idx % Wp, r1 = idx / Wp, m = r1 % Ho, r2 = r1 / Ho, t = r2 % T, b = r2 / T;
     float o[2][4];
 #pragma unroll
@@ -512,44 +517,54 @@ __global__ void __launch_bounds__(128) d3d_first_bwd_x2_kernel(const __nv_bfloat
     for (int kt = 0; kt < 3; ++kt) {
         const int to = t - kt + 1;
         if (to < 0 || to >= T) continue;
-        const __nv_bfloat16* base = dpre + (((static_cast<size_t>(b) * T + to) * Ho + m) * Wo + 2 * j) * 32;
+        const __nv_bfloat16* base = dpre + (((static_cast<size_t>(b) * T + to) * Ho + m) * Wo + 2 * j) * 32 + ch * 8;
+        float d[2][3][8];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            float d[2][3][8];
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int cc = 0; cc < 3; ++cc) {
+                const bool ok = (r == 0 || row1) && (cc < 2 || col2);
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) q = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(r) * Wo + cc) * 32));
+                const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    const bool ok = (r == 0 || row1) && (cc < 2 || col2);
-                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                    if (ok) q = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(r) * Wo + cc) * 32 + ch * 8));
-                    const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 f = unpack_bf16x2(qq[k]);
-                        d[r][cc][2 * k] = f.x; d[r][cc][2 * k + 1] = f.y;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = unpack_bf16x2(qq[k]);
+                    d[r][cc][2 * k] = f.x; d[r][cc][2 * k + 1] = f.y;
                 }
+            }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4* wp = reinterpret_cast<const float4*>(sw + (kt * 32 + ch * 8 + c) * 12);
-                const float4 wa = wp[0], wb = wp[1], wc = wp[2];
-                // w[ky][kx]: wa = (00 01 02 10), wb = (11 12 20 21), wc.x = 22
-                const float w00 = wa.x, w01 = wa.y, w02 = wa.z, w10 = wa.w, w11 = wb.x, w12 = wb.y, w20 = wb.z, w21 = wb.w, w22 = wc.x;
+        for (int c = 0; c < 8; ++c) {
+            const float4* wp = reinterpret_cast<const float4*>(sw + kt * 400 + ch * 100 + c * 12);
+            const float4 wa = wp[0], wb = wp[1], wc = wp[2];
+            // w[ky][kx]: wa = (00 01 02 10), wb = (11 12 20 21), wc.x = 22
+            const float w00 = wa.x, w01 = wa.y, w02 = wa.z, w10 = wa.w, w11 = wb.x, w12 = wb.y, w20 = wb.z, w21 = wb.w, w22 = wc.x;
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {       // 2x2 block n: gradient columns n, n+1 -> dx columns 2n, 2n+1
-                    const float d00 = d[0][n][c], d01 = d[0][n + 1][c], d10 = d[1][n][c], d11 = d[1][n + 1][c];
-                    o[0][2 * n] = fmaf(d00, w11, o[0][2 * n]);
-                    o[0][2 * n + 1] = fmaf(d00, w12, fmaf(d01, w10, o[0][2 * n + 1]));
-                    o[1][2 * n] = fmaf(d00, w21, fmaf(d10, w01, o[1][2 * n]));
-                    o[1][2 * n + 1] = fmaf(d00, w22, fmaf(d01, w20, fmaf(d10, w02, fmaf(d11, w00, o[1][2 * n + 1]))));
-                }
+            for (int n = 0; n < 2; ++n) {       // 2x2 block n: gradient columns n, n+1 -> dx columns 2n, 2n+1
+                const float d00 = d[0][n][c], d01 = d[0][n + 1][c], d10 = d[1][n][c], d11 = d[1][n + 1][c];
+                o[0][2 * n] = fmaf(d00, w11, o[0][2 * n]);
+                o[0][2 * n + 1] = fmaf(d00, w12, fmaf(d01, w10, o[0][2 * n + 1]));
+                o[1][2 * n] = fmaf(d00, w21, fmaf(d10, w01, o[1][2 * n]));
+                o[1][2 * n + 1] = fmaf(d00, w22, fmaf(d01, w20, fmaf(d10, w02, fmaf(d11, w00, o[1][2 * n + 1]))));
             }
         }
     }
-    float* op = dx + ((static_cast<size_t>(b) * T + t) * H + 2 * m) * W + 4 * j;
-    *reinterpret_cast<float4*>(op) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-    *reinterpret_cast<float4*>(op + W) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    // fold the four channel chunks (lane bits 0..1); afterwards lane q of the group stores quarter q: row q>>1, columns 2(q&1)..
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = o[r][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            o[r][c] = v;
+        }
+    if (!live) return;
+    const int rr = ch >> 1, c0 = (ch & 1) * 2;
+    float* op = dx + ((static_cast<size_t>(b) * T + t) * H + 2 * m + rr) * W + 4 * j + c0;
+    const float v0 = rr ? (c0 ? o[1][2] : o[1][0]) : (c0 ? o[0][2] : o[0][0]);
+    const float v1 = rr ? (c0 ? o[1][3] : o[1][1]) : (c0 ? o[0][3] : o[0][1]);
+    *reinterpret_cast<float2*>(op) = make_float2(v0, v1);
 }
 
 // dx[b,c,y,x] += g[b,y,x,c] for c < C (unpacks the padded 64-channel input gradient of d2d.0)
@@ -682,7 +697,7 @@ extern "C" int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* 
     if (dx) {
         const long long total = static_cast<long long>(B) * T * H * W;
         if (W % 4 == 0 && H % 2 == 0) {
-            d3d_first_bwd_x2_kernel<<<static_cast<unsigned>((total / 8 + 127) / 128), 128, 0, as_stream(stream)>>>(
+            d3d_first_bwd_x2_kernel<<<static_cast<unsigned>((total / 2 + 255) / 256), 256, 0, as_stream(stream)>>>(
                 static_cast<const __nv_bfloat16*>(dpre), w, sigma, dx, B, T, H, W);
             P2I_CHECK_LAUNCH("d3d_first_bwd_x2_kernel");
             return P2I_OK;

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
+    float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c8 = static_cast<int>(idx % cg);
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
             const float d0 = (fmaf(s, u0, bb[2 * i]) > 0.f) ? gg.x : 0.f;
             const float d1 = (fmaf(s, u1, bb[2 * i + 1]) > 0.f) ? gg.y : 0.f;
             ds += d0 * u0 + d1 * u1;
-            if (d0 != 0.f) atomicAdd(&s_db[c8 * 8 + 2 * i], d0);
-            if (d1 != 0.f) atomicAdd(&s_db[c8 * 8 + 2 * i + 1], d1);
+            dbv[2 * i] += d0;          // the thread keeps its channel group for the whole loop (stride % cg == 0)
+            dbv[2 * i + 1] += d1;
             ov[i] = pack_bf16x2(s * d0, s * d1);
         }
         reinterpret_cast<uint4*>(gout)[o] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
@@ -150,6 +151,19 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
         for (int off = span >> 1; off > 0; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
         if ((threadIdx.x & (span - 1)) == 0 && ds != 0.f)
             atomicAdd(&dpos[static_cast<size_t>(Y) * W2 + X], ds * s * (1.f - 0.5f * s));
+    }
+    // bias gradient: registers -> (lanes sharing a channel group folded by shuffles when cg < 32) -> shared -> global
+    {
+        const int c8 = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) % cg);
+        for (int off = 16; off >= cg; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dbv[k] += __shfl_xor_sync(0xffffffffu, dbv[k], off);
+        }
+        if (cg >= 32 || (threadIdx.x & 31) < cg) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (dbv[k] != 0.f) atomicAdd(&s_db[c8 * 8 + k], dbv[k]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x)
@@ -310,17 +324,23 @@ __global__ void __launch_bounds__(256) pyramid_bwd_kernel(const __nv_bfloat16* _
 //   dx [B,16,H,W] f32 : transposed grouped conv + the repeat_interleave(4) path
 //   dw [64,4,9]   f32 : sum_pix dy[pix][oc] * x[g*4+icl][pix + tap]   (register-tiled, atomics at the end)
 // ------------------------------------------------------------------------------------------------
+// lane = (pixel, group): the four lanes of a pixel read its 128 contiguous gradient bytes, so a warp request covers
+// 8 pixels x 128 B = 8 cache lines (one pixel per lane with a fixed group touched 32).  Weights: [g][tap][oc][ci] with a
+// group pitch of 580 floats so that the four groups of a warp read disjoint banks (LDS.128 broadcast per group).
 __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int H, int W) {
-    __shared__ __align__(16) float sw[9 * 16 * 4];            // this block's group: [tap][oc][ci] -> one LDS.128 per 4 FMAs
-    const int b = blockIdx.z >> 2, g = blockIdx.z & 3, yy = blockIdx.y;
-    for (int i = threadIdx.x; i < 9 * 16 * 4; i += blockDim.x) {
-        const int ci = i & 3, oc = (i >> 2) & 15, tap = i >> 6;
-        sw[i] = w[((g * 16 + oc) * 4 + ci) * 9 + tap];
+    __shared__ __align__(16) float sw[4 * 580];
+    for (int i = threadIdx.x; i < 4 * 576; i += blockDim.x) {
+        const int ci = i & 3, oc = (i >> 2) & 15, r = i >> 6, tap = r % 9, g = r / 9;
+        sw[g * 580 + (tap * 16 + oc) * 4 + ci] = w[((g * 16 + oc) * 4 + ci) * 9 + tap];
     }
     __syncthreads();
-    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.z;
+    const int g = threadIdx.x & 3;
+    const int xx = blockIdx.x * 32 + (threadIdx.x >> 2);
     if (xx >= W) return;
+    const size_t HW = static_cast<size_t>(H) * W;
+    for (int yy = blockIdx.y * 4; yy < H && yy < blockIdx.y * 4 + 4; ++yy) {      // 4 rows per block amortise the weight load
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* _
             const uint4* dp = reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * H + oy) * W + ox) * 64 + g * 16);
             const uint4 u0 = __ldg(dp), u1 = __ldg(dp + 1);
             const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            const float4* wt = reinterpret_cast<const float4*>(sw) + (ky * 3 + kx) * 16;
+            const float4* wt = reinterpret_cast<const float4*>(sw + g * 580) + (ky * 3 + kx) * 16;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 f = unpack_bf16x2(uu[i]);
@@ -349,9 +369,9 @@ __global__ void __launch_bounds__(128) stem_bwd_dx_kernel(const __nv_bfloat16* _
             }
         }
     }
-    const size_t HW = static_cast<size_t>(H) * W;
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) dx[(static_cast<size_t>(b) * 16 + g * 4 + ci) * HW + static_cast<size_t>(yy) * W + xx] = acc[ci];
+    }
 }
 
 // Weight gradient, tiled: a block stages one image-row segment (64 pixels: the 16 x 3 x 66 input patch and the
@@ -497,12 +517,12 @@ extern "C" int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx
 extern "C" int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W,
                             void* stream) {
     P2I_CHECK_ARG(dy && x && w && dx && dw, "stem_bwd: null pointer");
-    dim3 grid(cdiv(W, 128), H, B * 4);
+    dim3 grid(cdiv(W, 32), cdiv(H, 4), B);
     stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
     P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");
     long long tiles = static_cast<long long>(B) * H * ((W + 63) / 64);
     P2I_CHECK_ARG(tiles < (1ll << 31), "stem_bwd: tensor too large");
-    if (tiles > sm_count() * 2) tiles = sm_count() * 2;
+    if (tiles > sm_count() * 4) tiles = sm_count() * 4;
     stem_bwd_dw2_kernel<<<static_cast<unsigned>(tiles), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
     P2I_CHECK_LAUNCH("stem_bwd_dw2_kernel");
     return P2I_OK;

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(1024) points_extract_kernel(const float* __res
     const int s0 = warp * seg, s1 = min(Q, s0 + seg);
     const bool vec = (Q & 3) == 0 && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
     int cnt = 0;
+#pragma unroll 8
     for (int i = s0 + lane * 4; i < s1; i += 128) {
         int f = 0;
         if (vec) {
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(1024) points_extract_kernel(const float* __res
     }
     if (threadIdx.x == 0) counts[b] = total < cap ? total : cap;
     if (cnt == 0) return;                                             // warp-uniform
+#pragma unroll 4
     for (int i0 = s0; i0 < s1; i0 += 128) {                           // warp-uniform trip count (shuffles inside)
         const int i = i0 + lane * 4;
         int flags = 0;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(1024) points_extract_kernel(const float* __res
                 for (int j = 0; j < 4; ++j) flags |= (i + j < s1 && m[i + j] > 0.f) << j;
             }
         }
+        if (__ballot_sync(0xffffffffu, flags != 0) == 0u) continue;   // sparse masks: most 128-element rounds are empty
         const int c = __popc(flags);
         int incl = c;
 #pragma unroll
