@@ -274,7 +274,13 @@ def run_ours(args):
     else:
         G.eval()
     # four rotating batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
-    batches = [tuple(t.to(dev) for t in synth.make_batch(B, T, H, W, N_OBS, 1000 * rank + i)) for i in range(4)]
+    # frames differ per batch and rank; the gauge mask is ONE static 79-pixel pattern (seed 1), as the reference's 'stis'
+    # mask file is (data/sti_dataset.py:104-117, SURVEY.md 8d inputs 2-3)
+    mask = synth.make_mask(B, T, H, W, N_OBS, 1)
+    batches = []
+    for i in range(4):
+        fr = synth.make_batch(B, T, H, W, N_OBS, 1000 * rank + i)[0]
+        batches.append(tuple(t.to(dev) for t in (fr, fr * mask, mask)))
     host = [tuple(t.cpu().pin_memory() for t in b) for b in batches[:2]]
     out_host = torch.empty(B, T, 1, H, W, dtype=torch.float32).pin_memory()
     loss_host = torch.empty(6, dtype=torch.float32).pin_memory()
@@ -415,7 +421,7 @@ def run_ours(args):
             "metric": metric, "value": events / (ms * 1e-3), "unit": "events/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS,
+            "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS, "gauge_mask": "one static pattern (stis), seed 1",
                        "weights": "random init seed 2024",
                        "launch": "eager" if graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train) else "CUDA graph replay"),
                        "e2e_pipeline": "H2D / step / D2H on three streams, double-buffered",
@@ -425,7 +431,7 @@ def run_ours(args):
                              "far above the 126 MB L2"},
             "e2e": {"value": events / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: forward + data-gradient launches)",
+            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient launches)",
                          "achieved": ig_tf, "peak": sustained, "unit": "TFLOP/s", "frac": (ig_tf / sustained) if ig_tf else None,
                          "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                          "kernel_ms_per_step": ig_ms / psteps, "launches_per_step": ig_n // psteps,

@@ -339,6 +339,14 @@ int p2i_adam_chunk_elems(void);
 int p2i_window_blend(const float* preds, float* out, int L, int HW, int stride, int step, int n_win, float scale,
                      void* stream);
 
+/* Device-side batch preparation (STIDataset.post_process, p2igan_bench/data/sti_dataset.py:203-229, and
+ * Trainer._prepare_batch, scripts/train.py:468-473): frames_u8 [B,T,H0,W0] uint8 -> frames = u8/255 (IEEE fp32
+ * division, as numpy), masked = frames * mask, masks in {0,1}; all three f32 [B,T,1,H,W], centre-cropped from
+ * (H0,W0) to (H,W) with start (old-new)//2.  mask_u8: non-zero = observed; mask_mode 0: one [H0,W0] pattern
+ * ('sti'/'stis' file masks), 1: [B,H0,W0], 2: [B,T,H0,W0]. */
+int p2i_batch_prep_u8(const void* frames_u8, const void* mask_u8, float* frames, float* masked, float* masks, int B, int T,
+                      int H0, int W0, int H, int W, int mask_mode, void* stream);
+
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);
 int p2i_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, void* stream);

@@ -553,3 +553,26 @@ def sliding_window_infer(sd: State, masked: Tensor, masks: Tensor, stride: int =
         acc[s:s + valid] += out[0, :valid]
         cnt[s:s + valid] += 1
     return torch.clamp(acc / torch.clamp(cnt, min=1e-5) * output_scale, min=0.0)
+
+
+# ----------------------------------------------------------------------------------------------- batch preparation
+def batch_post_process(video_u8, mask_u8, height: int, width: int):
+    """numpy restatement of the host-side sample preparation (p2igan_bench/data/sti_dataset.py:203-243:
+    ``astype(float32) / 255.0``, ``masked = video * mask``, ``_crop_center`` with start ``max((old - new) // 2, 0)``)
+    followed by ``Trainer._prepare_batch``'s channel permute (scripts/train.py:468-473).
+    video_u8 [B,T,H0,W0] uint8; mask_u8 [H0,W0] | [B,H0,W0] | [B,T,H0,W0] (non-zero = observed)
+    -> (frames, masked, masks) float32 numpy arrays [B,T,1,height,width]."""
+    import numpy as np
+    v = np.asarray(video_u8)
+    B, T, H0, W0 = v.shape
+    m = np.asarray(mask_u8) != 0
+    if m.ndim == 2:
+        m = np.broadcast_to(m[None, None], v.shape)
+    elif m.ndim == 3:
+        m = np.broadcast_to(m[:, None], v.shape)
+    frames = v.astype(np.float32) / np.float32(255.0)
+    mask = m.astype(np.float32)
+    masked = frames * mask
+    y0, x0 = max((H0 - height) // 2, 0), max((W0 - width) // 2, 0)
+    crop = lambda a: np.ascontiguousarray(a[:, :, y0:y0 + height, x0:x0 + width])[:, :, None]   # noqa: E731
+    return crop(frames), crop(masked), crop(mask)
