@@ -124,6 +124,31 @@ def test_input_block_empty_and_single_point():
     assert float((out - ref).abs().max()) < 2e-5
 
 
+def test_input_block_neighbour_cache_follows_mask_changes():
+    """The cross-call neighbour-table cache (keyed on sample 0's points, decided on the device) must never serve a
+    stale table: mask A, A again (cache hit), B (miss), A (miss), sample 0 empty, A -- every call vs the oracle."""
+    from p2igan_b200 import build_generator
+    torch.manual_seed(4)
+    G = build_generator(synth.make_cfg(32, 32))
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    G = G.to(DEV)
+    B, H, W = 2, 32, 32
+
+    def case(seed_frames, seed_mask, empty0=False):
+        fr = synth.make_batch(B, 16, H, W, 12, seed_frames)[0].reshape(B, 16, H, W)
+        mk = synth.make_mask(B, 16, H, W, 12, seed_mask).reshape(B, 16, H, W).clone()
+        if empty0:
+            mk[0] = 0
+        return fr * mk, mk
+
+    for sf, sm, e0 in [(1, 50, False), (2, 50, False), (3, 51, False), (4, 50, False), (5, 50, True), (6, 50, False)]:
+        mf, mk = case(sf, sm, e0)
+        ref = O.input_block(sd, mf, mk, idw="exact")
+        with torch.no_grad():
+            out = G.input(mf.to(DEV), mk.to(DEV)).cpu()
+        assert float((out - ref).abs().max()) < 2e-5, (sf, sm, e0)
+
+
 def _generator_pair(H, W, seed_model, perturb):
     from p2igan_b200 import build_generator
     torch.manual_seed(seed_model)
