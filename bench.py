@@ -287,9 +287,13 @@ def run_ours(args):
     D = build_discriminator(cfg).to(dev) if train else None
     if train:
         G.train(); D.train()
-        ts = GANTrainStep(cfg, G, D)
+        # gradient exchange between ranks: "peer" = one NVLink peer-memory all-reduce kernel per model inside the step's
+        # single CUDA graph (p2igan_b200/peer.py); "nccl" = two NCCL all-reduces between three CUDA graphs
+        exchange = os.environ.get("P2I_DP_EXCHANGE", "peer") if world > 1 else "none"
+        ts = GANTrainStep(cfg, G, D, peer_exchange=(exchange == "peer"))
     else:
         G.eval()
+        exchange = "none"
     # four rotating batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
     # frames differ per batch and rank; the gauge mask is ONE static 79-pixel pattern (seed 1), as the reference's 'stis'
     # mask file is (data/sti_dataset.py:104-117, SURVEY.md 8d inputs 2-3)
@@ -319,7 +323,7 @@ def run_ours(args):
     # training replays three graphs with the two NCCL all-reduces between them (GraphedDPStep).
     graphed = None
     if not args.no_graph:
-        if world > 1 and train:
+        if world > 1 and train and exchange != "peer":
             dp = GraphedDPStep(ts, batches[0], warmup=3)
 
             class _DP:
@@ -419,6 +423,9 @@ def run_ours(args):
     timer.remove()
     ev_ms = ConvTimer.event_pair_overhead_ms()
 
+    if train and ts.peer_exchange:
+        ts.flat_g.peer.check()           # no exchange timed out
+        ts.flat_d.peer.check()
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -444,9 +451,11 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS, "gauge_mask": "one static pattern (stis), seed 1",
                        "weights": "random init seed 2024",
-                       "launch": "eager" if graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train) else "CUDA graph replay"),
+                       "launch": "eager" if graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train and exchange != "peer") else "CUDA graph replay"),
                        "e2e_pipeline": "H2D / step / D2H on three streams, double-buffered",
-                       "parallelism": (f"data parallel over {world} GPU(s): flat NCCL all-reduce of D and G gradients" if train
+                       "parallelism": ((f"data parallel over {world} GPU(s): flat D and G gradient buffers, " +
+                                        ("NVLink peer-memory all-reduce kernel (CUDA IPC) inside the step graph" if exchange == "peer"
+                                         else "NCCL all-reduce")) if train
                                        else f"events sharded over {world} GPU(s), no collective"),
                        "l2": "no explicit flush: 4 rotating input batches and a per-step activation working set of several GB, "
                              "far above the 126 MB L2"},

@@ -347,6 +347,28 @@ int p2i_window_blend(const float* preds, float* out, int L, int HW, int stride, 
 int p2i_batch_prep_u8(const void* frames_u8, const void* mask_u8, float* frames, float* masked, float* masks, int B, int T,
                       int H0, int W0, int H, int W, int mask_mode, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (replaces the bucketed NCCL all-reduce of
+ * torch DDP, which the reference would use -- it has no multi-GPU path of its own).
+ * Set-up (the only entry points of this library that allocate or touch other processes): each rank allocates its flat
+ * gradient buffer and a flag array with p2i_peer_alloc (cudaMalloc + zero fill), exports both with p2i_peer_export (64-byte
+ * CUDA IPC handle), exchanges the handles out of band (torch.distributed.all_gather_object) and maps the peers' with
+ * p2i_peer_import.  p2i_peer_allreduce then sums the N buffers in place on every rank with ONE kernel per rank
+ * (two-shot: reduce-scatter + all-gather by direct peer loads, block-level flag barriers, fixed summation order ->
+ * bitwise identical results on all ranks).  bufs / flags: HOST arrays of `world` device pointers as mapped in this
+ * process (index = rank; the own entries are the local allocations).  epoch_dev / err_dev: local device ints (zero
+ * initialised); *err_dev becomes 1 if a peer did not show up within ~10 s (the kernel then finishes instead of hanging).
+ * CUDA-graph capturable; all ranks must call it the same number of times.
+ * ------------------------------------------------------------------------------------------- */
+int p2i_peer_alloc(void** out, long long bytes);
+int p2i_peer_free(void* p);
+int p2i_peer_export(const void* p, void* handle64);
+int p2i_peer_import(const void* handle64, void** out);
+int p2i_peer_close(void* p);
+int p2i_peer_flags_bytes(void);
+int p2i_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, long long n, int* epoch_dev, int* err_dev,
+                       void* stream);
+
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);
 int p2i_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int C, int H, int W, void* stream);

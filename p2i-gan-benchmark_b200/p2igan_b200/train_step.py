@@ -25,12 +25,21 @@ from .optim import FusedAdam
 
 
 class FlatGrads:
-    """Flat fp32 gradient buffer; ``p.grad`` of every given parameter becomes a view into it."""
+    """Flat fp32 gradient buffer; ``p.grad`` of every given parameter becomes a view into it.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    ``peer=True`` (multi-GPU, one node): the buffer is a CUDA-IPC allocation mapped by every rank and ``all_reduce`` is
+    ONE peer-memory kernel (``peer.PeerAllReduce``, CUDA-graph capturable) instead of an NCCL collective."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], peer: bool = False, group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.peer = None
+        if peer:
+            from .peer import PeerAllReduce
+            self.peer = PeerAllReduce(n, group)
+            self.flat = self.peer.tensor[:n]
+        else:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
         o = 0
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view(p.shape)
@@ -46,12 +55,15 @@ class FlatGrads:
         world = dist.get_world_size(group)
         if world == 1:
             return 1.0
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if self.peer is not None:
+            self.peer.all_reduce()
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         return 1.0 / world
 
 
 class GANTrainStep:
-    def __init__(self, cfg: Dict[str, Any], generator, discriminator=None, process_group=None):
+    def __init__(self, cfg: Dict[str, Any], generator, discriminator=None, process_group=None, peer_exchange: bool = False):
         self.cfg = cfg
         self.G, self.D = generator, discriminator
         loss_cfg = cfg.get("loss", {})
@@ -64,12 +76,15 @@ class GANTrainStep:
         oc = cfg["train"]["optimizer"]
         betas = (oc.get("beta1", 0.0), oc.get("beta2", 0.99))
         self.pg = process_group
-        self.flat_g = FlatGrads(generator.parameters())
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.peer_exchange = bool(peer_exchange and multi)
+        self.flat_g = FlatGrads(generator.parameters(), peer=self.peer_exchange, group=process_group)
         self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
         self.flat_d = self.opt_d = None
         if self.use_gan:
             # alpha3d never receives a gradient in the reference (unused Parameter, models/p2igan.py:145): keep grad None
-            self.flat_d = FlatGrads(p for n, p in discriminator.named_parameters() if n != "alpha3d")
+            self.flat_d = FlatGrads((p for n, p in discriminator.named_parameters() if n != "alpha3d"), peer=self.peer_exchange,
+                                    group=process_group)
             self.opt_d = FusedAdam(self.flat_d.params, lr=oc["lr"], betas=betas)
             from . import disc_bwd
             disc_bwd.prepare(discriminator)

@@ -1,0 +1,115 @@
+"""torchrun worker (>= 2 GPUs on one node): p2i_peer_allreduce vs NCCL all-reduce, eager and as a CUDA-graph replay,
+then one data-parallel GAN training step with the peer exchange vs the NCCL exchange.  Prints PEER_OK on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_peer_allreduce.py
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "p2i-gan-benchmark_b200")):
+    sys.path.insert(0, p)
+import torch
+import torch.distributed as dist
+
+import synth
+from p2igan_b200.peer import PeerAllReduce
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+
+def check(n):
+    ar = PeerAllReduce(n)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for it in range(3):
+        x = torch.randn(n, device=dev, generator=g)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        ar.tensor[:n].copy_(x)
+        ar.all_reduce()
+        torch.cuda.synchronize()
+        ar.check()
+        d = float((ar.tensor[:n] - ref).abs().max())
+        assert d <= 1e-5 * world, (n, it, d)
+        # every rank holds bitwise the same sum
+        mine = ar.tensor[:n].clone()
+        other = mine.clone()
+        dist.broadcast(other, 0)
+        assert torch.equal(mine, other), (n, it)
+    # graph replay
+    x = torch.randn(n, device=dev, generator=g)
+    torch.cuda.synchronize()
+    dist.barrier()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        ar.tensor[:n].copy_(x)
+        ar.all_reduce()
+    ref = x.clone()
+    dist.all_reduce(ref)
+    for _ in range(3):
+        gr.replay()
+    torch.cuda.synchronize()
+    ar.check()
+    assert float((ar.tensor[:n] - ref).abs().max()) <= 1e-5 * world
+    # timing (in place, values grow: irrelevant)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ar.all_reduce()
+    e1.record()
+    torch.cuda.synchronize()
+    t_peer = e0.elapsed_time(e1) / 20
+    y = torch.randn(n, device=dev)
+    for _ in range(3):
+        dist.all_reduce(y)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        dist.all_reduce(y)
+    e1.record()
+    torch.cuda.synchronize()
+    t_nccl = e0.elapsed_time(e1) / 20
+    if rank == 0:
+        print(f"n={n:9d} ({n * 4 / 1e6:6.1f} MB)  peer {t_peer * 1e3:7.1f} us   nccl {t_nccl * 1e3:7.1f} us", flush=True)
+    return ar
+
+
+keep = [check(n) for n in (1024, 1690884, 25887984)]
+
+
+def train_losses(peer):
+    from p2igan_b200 import build_discriminator, build_generator
+    from p2igan_b200.train_step import GANTrainStep
+    cfg = synth.make_cfg(32, 32)
+    torch.manual_seed(2024)
+    G, D = build_generator(cfg).to(dev).train(), build_discriminator(cfg).to(dev).train()
+    ts = GANTrainStep(cfg, G, D, peer_exchange=peer)
+    out = []
+    for i in range(2):
+        b = tuple(t.to(dev) for t in synth.make_batch(2, 16, 32, 32, 12, 500 + 10 * rank + i))
+        out.append({k: float(v) for k, v in ts.step(*b).items()})
+    fp = torch.cat([p.detach().reshape(-1) for p in G.parameters()])
+    return out, fp
+
+
+ln, pn = train_losses(False)
+lp, pp = train_losses(True)
+for a, b in zip(ln, lp):
+    for k in a:
+        assert abs(a[k] - b[k]) < 1e-2 * abs(a[k]) + 1e-5, (k, a[k], b[k])
+d = (pn - pp).abs()
+assert float(d.max()) <= 3e-3 and float(d.mean()) < 2e-5, (float(d.max()), float(d.mean()))
+# data-parallel invariant: parameters stay identical across ranks
+ref = pp.clone()
+dist.broadcast(ref, 0)
+assert torch.equal(ref, pp), "parameters diverged across ranks"
+dist.barrier()
+if rank == 0:
+    print("PEER_OK", flush=True)
+dist.destroy_process_group()

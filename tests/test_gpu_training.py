@@ -291,3 +291,16 @@ def test_three_graph_dp_step_equals_eager_step():
         assert float(d.max()) <= 3e-3, (k, float(d.max()))
         tot += float(d.sum()); num += d.numel()
     assert tot / num < 2e-5, tot / num
+
+
+def test_peer_allreduce_two_gpus():
+    """NVLink peer-memory all-reduce vs NCCL, graph replay, and a DP training step (tests/run_peer_allreduce.py under torchrun)."""
+    import subprocess
+    import sys as _sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on one node")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_peer_allreduce.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
