@@ -59,60 +59,106 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& a, int phase, int 
     __syncthreads();
 }
 
+// WT = world size known at compile time (2, 4, 8: the peer loop is fully unrolled so that the loads from ALL peers are in
+// flight together -- with a run-time trip count each peer's load waited for the previous peer's add) or 0 = generic.
+template <int WT>
 __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerTable a) {
     const int epoch = *a.epoch;
-    const int W = a.world, G = gridDim.x;
+    const int W = WT ? WT : a.world, G = gridDim.x;
     const long long n4 = a.n >> 2;
     const long long shard4 = (n4 + W - 1) / W;                 // float4 per shard
     const long long per4 = (shard4 + G - 1) / G;               // float4 per (shard, block)
     const long long lo = static_cast<long long>(blockIdx.x) * per4;
     const long long hi = (lo + per4 < shard4) ? lo + per4 : shard4;
+    constexpr int U = WT == 8 ? 2 : 4;                          // independent 16-byte loads per peer and thread
 
     peer_barrier(a, 0, epoch);
     {
-        // 4 independent 16-byte loads per peer and thread in flight (NVLink latency ~2-3 us)
         const long long s0 = static_cast<long long>(a.rank) * shard4;
         float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]);
-        for (long long i = lo + threadIdx.x; i < hi; i += 4 * PEER_THREADS) {
-            float4 acc[4];
-            long long j[4];
+        for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
+            bool ok[U];
+            long long j[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 j[u] = s0 + i + u * PEER_THREADS;
-                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ok[u] = i + u * PEER_THREADS < hi && j[u] < n4;
             }
-            for (int r = 0; r < W; ++r) {
-                const float4* src = reinterpret_cast<const float4*>(a.buf[r]);
-                float4 v[4];
+            float4 acc[U];
+            if (WT) {
+                float4 v[WT ? WT : 1][U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = (i + u * PEER_THREADS < hi && j[u] < n4) ? __ldcg(src + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < WT; ++r)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                    for (int u = 0; u < U; ++u)
+                        v[r][u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(a.buf[r]) + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    acc[u] = v[0][u];
+#pragma unroll
+                    for (int r = 1; r < WT; ++r) { acc[u].x += v[r][u].x; acc[u].y += v[r][u].y; acc[u].z += v[r][u].z; acc[u].w += v[r][u].w; }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < W; ++r) {
+                    const float4* src = reinterpret_cast<const float4*>(a.buf[r]);
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) v[u] = ok[u] ? __ldcg(src + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * PEER_THREADS < hi && j[u] < n4) dst[j[u]] = acc[u];
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) dst[j[u]] = acc[u];
         }
     }
     peer_barrier(a, 1, epoch);
     {
         float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]);
-        for (int k = 1; k < W; ++k) {
-            const int s = (a.rank + k) % W;                    // start with different owners on different ranks
-            const long long s0 = static_cast<long long>(s) * shard4;
-            const float4* src = reinterpret_cast<const float4*>(a.buf[s]);
-            for (long long i = lo + threadIdx.x; i < hi; i += 4 * PEER_THREADS) {
-                float4 v[4];
+        if (WT) {
+            // all W-1 owners' sub-ranges in flight together
+            for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
+                float4 v[WT ? WT : 1][U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long j = s0 + i + u * PEER_THREADS;
-                    v[u] = (i + u * PEER_THREADS < hi && j < n4) ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 1; k < WT; ++k) {
+                    const int s = (a.rank + k) % (WT ? WT : 1);
+                    const float4* src = reinterpret_cast<const float4*>(a.buf[s]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const long long j = static_cast<long long>(s) * shard4 + i + u * PEER_THREADS;
+                        v[k][u] = (i + u * PEER_THREADS < hi && j < n4) ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long j = s0 + i + u * PEER_THREADS;
-                    if (i + u * PEER_THREADS < hi && j < n4) dst[j] = v[u];
+                for (int k = 1; k < WT; ++k) {
+                    const int s = (a.rank + k) % (WT ? WT : 1);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const long long j = static_cast<long long>(s) * shard4 + i + u * PEER_THREADS;
+                        if (i + u * PEER_THREADS < hi && j < n4) dst[j] = v[k][u];
+                    }
+                }
+            }
+        } else {
+            for (int k = 1; k < W; ++k) {
+                const int s = (a.rank + k) % W;                    // start with different owners on different ranks
+                const long long s0 = static_cast<long long>(s) * shard4;
+                const float4* src = reinterpret_cast<const float4*>(a.buf[s]);
+                for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const long long j = s0 + i + u * PEER_THREADS;
+                        v[u] = (i + u * PEER_THREADS < hi && j < n4) ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const long long j = s0 + i + u * PEER_THREADS;
+                        if (i + u * PEER_THREADS < hi && j < n4) dst[j] = v[u];
+                    }
                 }
             }
         }
@@ -180,7 +226,10 @@ extern "C" int p2i_peer_allreduce(void* const* bufs, void* const* flags, int ran
     if (grid > PEER_MAX_BLOCKS) grid = PEER_MAX_BLOCKS;
     peer_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(epoch_dev);
     P2I_CHECK_LAUNCH("peer_tick_kernel");
-    peer_allreduce_kernel<<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
+    if (world == 2) peer_allreduce_kernel<2><<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
+    else if (world == 4) peer_allreduce_kernel<4><<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
+    else if (world == 8) peer_allreduce_kernel<8><<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
+    else peer_allreduce_kernel<0><<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
     P2I_CHECK_LAUNCH("peer_allreduce_kernel");
     return P2I_OK;
 }
