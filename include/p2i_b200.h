@@ -334,6 +334,13 @@ int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 int p2i_adam_chunk_elems(void);
 
+/* SSIM of RegressionMetrics (metric.py:36,55-56,69 -> torchmetrics StructuralSimilarityIndexMeasure(data_range):
+ * 11x11 gaussian window, sigma 1.5, k1 0.01, k2 0.03, per-image mean over the (H-10)x(W-10) interior, mean over images).
+ * PARITY UNPINNED: torchmetrics 1.0.3 is absent from the reference tree and this image; restated from its published
+ * algorithm.  pred/target f32 [N,H,W]; state f64 [2] += {sum of per-image SSIM, N}. */
+int p2i_ssim_update(const float* pred, const float* target, int N, int H, int W, int apply_transform, float data_range,
+                    double* state, void* stream);
+
 /* Sliding-window blend of scripts/infer.py:237-245: preds f32 [n_win, stride, HW] (window w starts at frame w*step) ->
  * out f32 [L, HW] = clip(scale * mean over covering windows, 0). */
 int p2i_window_blend(const float* preds, float* out, int L, int HW, int stride, int step, int n_win, float scale,

@@ -415,12 +415,38 @@ def rain_rate(x: Tensor) -> Tensor:
     return torch.pow(10.0, x * 0.0625) * 0.036
 
 
+def ssim_per_image(pred: Tensor, target: Tensor, data_range: float = 1.0, sigma: float = 1.5, k1: float = 0.01,
+                   k2: float = 0.03) -> Tensor:
+    """PARITY UNPINNED.  torchmetrics 1.0.3 (pinned by the reference's uv.lock:1162-1164; absent here) -- restatement of
+    its published ``functional/image/ssim.py::_ssim_update`` as called by StructuralSimilarityIndexMeasure(data_range)
+    (metric.py:36): gaussian window of size ``int(3.5*sigma+0.5)*2+1`` = 11, reflect padding by 5, grouped conv2d of
+    (p, t, p*p, t*t, p*t), SSIM map, crop of the padded border, mean per image.  pred/target [N,1,H,W] f32 -> [N]."""
+    ks = int(3.5 * sigma + 0.5) * 2 + 1
+    pad = (ks - 1) // 2
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    dist = torch.arange((1 - ks) / 2, (1 + ks) / 2, 1, dtype=torch.float32)
+    g = torch.exp(-torch.pow(dist / sigma, 2) / 2)
+    g = (g / g.sum()).unsqueeze(0)
+    kernel = torch.matmul(g.t(), g).expand(1, 1, ks, ks)
+    p = F.pad(pred, (pad, pad, pad, pad), mode="reflect")
+    t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
+    out = F.conv2d(torch.cat((p, t, p * p, t * t, p * t)), kernel)
+    n = pred.shape[0]
+    mu_p, mu_t, e_pp, e_tt, e_pt = (out[i * n:(i + 1) * n] for i in range(5))
+    mu_pp, mu_tt, mu_pt = mu_p * mu_p, mu_t * mu_t, mu_p * mu_t
+    s_p, s_t, s_pt = e_pp - mu_pp, e_tt - mu_tt, e_pt - mu_pt
+    full = ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_p + s_t + c2))
+    return full[..., pad:-pad, pad:-pad].reshape(n, -1).mean(-1)
+
+
 class MetricSuiteOracle:
-    """MAE/RMSE, POD/FAR/CSI/HSS per threshold, FSS per (threshold, scale).  SSIM is not restated
-    (torchmetrics is absent from this image; SURVEY.md 8c marks SSIM parity as unpinned)."""
+    """MAE/RMSE, POD/FAR/CSI/HSS per threshold, FSS per (threshold, scale), and SSIM ("ssim", parity unpinned:
+    ``ssim_per_image``; only reported when ``with_ssim`` so that the reference goldens, taken with a stubbed
+    torchmetrics, compare key for key)."""
 
     def __init__(self, thresholds: Sequence[float] = (0.5, 2.0, 4.0, 8.0), scales: Sequence[int] = (1, 2, 4, 8),
-                 apply_transform: bool = True):
+                 apply_transform: bool = True, with_ssim: bool = False, data_range: float = 1.0):
+        self.with_ssim, self.data_range = with_ssim, data_range
         self.thr = [float(t) for t in thresholds]
         self.scales = [int(s) for s in scales]
         self.apply_transform = apply_transform
@@ -433,6 +459,7 @@ class MetricSuiteOracle:
         self.cont = torch.zeros(len(self.thr), 4)                 # hits, misses, false, correct
         self.fss_sum = torch.zeros(len(self.thr), len(self.scales))
         self.fss_cnt = torch.zeros(len(self.thr), len(self.scales))
+        self.ssim_sum, self.ssim_n = torch.tensor(0.0), 0
 
     def update(self, pred: Tensor, target: Tensor):
         p32, t32 = pred.detach().float(), target.detach().float()
@@ -441,6 +468,10 @@ class MetricSuiteOracle:
         self.abs_sum += d.abs().sum()
         self.sq_sum += (d * d).sum()
         self.n += d.numel()
+        if self.with_ssim and pr.shape[-1] > 10 and pr.shape[-2] > 10:      # metric.py:55-56 (on the transformed values)
+            sp = ssim_per_image(pr.reshape(-1, 1, *pr.shape[-2:]), tr.reshape(-1, 1, *tr.shape[-2:]), self.data_range)
+            self.ssim_sum += sp.sum()
+            self.ssim_n += sp.numel()
         pc, tc = rain_rate(p32), rain_rate(t32)                   # categorical/FSS always transform
         H, W = pc.shape[-2:]
         pm, tm = pc.reshape(-1, 1, H, W), tc.reshape(-1, 1, H, W)
@@ -463,6 +494,8 @@ class MetricSuiteOracle:
     def compute(self) -> Dict[str, float]:
         n = torch.clamp(self.n, min=1.0)
         out = {"mae": float(self.abs_sum / n), "rmse": float(torch.sqrt(self.sq_sum / n))}
+        if self.with_ssim:
+            out["ssim"] = float(self.ssim_sum / self.ssim_n) if self.ssim_n else float("nan")
         for i, thr in enumerate(self.thr):
             h, m, f, c = self.cont[i]
             pre = f"cat_thr{thr:.2f}"

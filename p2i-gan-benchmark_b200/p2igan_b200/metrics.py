@@ -4,7 +4,8 @@
 ``.reset()`` keep the reference API and key names.  One fused kernel pass per update accumulates MAE/RMSE sums, the
 contingency tables of all thresholds and the FSS sums of all (threshold, scale) pairs; states are sum-reduced
 (``dist_reduce_fx="sum"`` in the reference), so multi-GPU evaluation shards events and all-reduces ``state`` once.
-SSIM (torchmetrics, absent from this image; parity unpinned) is reported as NaN.
+SSIM follows torchmetrics' published algorithm (gaussian 11x11, sigma 1.5; ``csrc/ssim.cu``); torchmetrics itself is absent
+from this image, so that one value is "parity unpinned" (SURVEY.md 8c).  Images smaller than the window report NaN.
 """
 from __future__ import annotations
 
@@ -55,6 +56,7 @@ class RainfallMetricSuite:
             raise RuntimeError("RainfallMetricSuite runs on CUDA (sm_100a) only; there is no CPU path")
         self.state = torch.zeros(51, dtype=torch.float32, device=self.device)
         self.scratch = torch.zeros(50, dtype=torch.float64, device=self.device)
+        self.ssim_state = torch.zeros(2, dtype=torch.float64, device=self.device)      # sum of per-image SSIM, images
         return self
 
     def update(self, preds: torch.Tensor, target: torch.Tensor) -> None:
@@ -69,16 +71,24 @@ class RainfallMetricSuite:
         N = p.numel() // (H * W)
         LIB.call("p2i_metrics_update", ptr(p), ptr(t), N, H, W, self._thr_c, len(self.thr), self._sc_c, len(self.scales),
                  1 if self.cfg.apply_transform else 0, ptr(self.scratch), ptr(self.state), stream())
+        if H > 10 and W > 10:
+            for i in range(0, N, 65535):
+                k = min(65535, N - i)
+                LIB.call("p2i_ssim_update", ptr(p.view(N, H, W)[i:]), ptr(t.view(N, H, W)[i:]), k, H, W,
+                         1 if self.cfg.apply_transform else 0, float(self.cfg.data_range), ptr(self.ssim_state), stream())
 
     def all_reduce(self, group=None) -> None:
         """Sum the streaming state over data-parallel ranks (the reference declares dist_reduce_fx='sum')."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.state, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.ssim_state, op=dist.ReduceOp.SUM, group=group)
 
     def compute(self) -> Dict[str, float]:
         s = self.state.detach().cpu()          # host synchronisation: compute() is outside the hot loop
         n = torch.clamp(s[2], min=1.0)
-        out: Dict[str, float] = {"mae": float(s[0] / n), "rmse": float(torch.sqrt(s[1] / n)), "ssim": float("nan")}
+        ss = self.ssim_state.detach().cpu()
+        ssim = float(ss[0] / ss[1]) if float(ss[1]) > 0 else float("nan")
+        out: Dict[str, float] = {"mae": float(s[0] / n), "rmse": float(torch.sqrt(s[1] / n)), "ssim": ssim}
         for i, thr in enumerate(self.thr):
             h, m, f, c = s[3 + 4 * i], s[4 + 4 * i], s[5 + 4 * i], s[6 + 4 * i]
             pre = f"cat_thr{thr:.2f}"
@@ -99,3 +109,4 @@ class RainfallMetricSuite:
         if self.state is not None:
             self.state.zero_()
             self.scratch.zero_()
+            self.ssim_state.zero_()

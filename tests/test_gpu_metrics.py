@@ -13,8 +13,8 @@ DEV = "cuda:0"
 
 
 def _compare(ours, ref, tol=1e-3):
-    assert set(ours) - {"ssim"} == set(ref)
-    assert math.isnan(ours["ssim"])
+    """ref without "ssim": reference golden taken with a stubbed torchmetrics (SSIM parity is unpinned)."""
+    assert set(ours) - {"ssim"} == set(ref) - {"ssim"}
     for k, v in ref.items():
         assert abs(ours[k] - v) < tol, (k, ours[k], v)
 
@@ -25,7 +25,7 @@ def test_metric_suite_matches_oracle(shape, scale):
     g = torch.Generator().manual_seed(3)
     pred = torch.rand(shape, generator=g) ** 2 * scale
     tgt = torch.rand(shape, generator=g) ** 2 * scale
-    ref = O.MetricSuiteOracle()
+    ref = O.MetricSuiteOracle(with_ssim=True)
     suite = RainfallMetricSuite(MetricConfig()).to(DEV)
     for a, b in ((pred, tgt), (tgt.flip(-1), tgt)):
         ref.update(a, b)
@@ -33,7 +33,7 @@ def test_metric_suite_matches_oracle(shape, scale):
     _compare(suite.compute(), ref.compute())
     suite.reset()
     suite.update(pred.to(DEV), tgt.to(DEV))
-    ref2 = O.MetricSuiteOracle()
+    ref2 = O.MetricSuiteOracle(with_ssim=True)
     ref2.update(pred, tgt)
     _compare(suite.compute(), ref2.compute())
 
@@ -58,6 +58,7 @@ def test_metric_suite_stress_256_and_properties():
     suite.update(x, x)
     m = suite.compute()
     assert m["mae"] == 0.0 and m["rmse"] == 0.0
+    assert abs(m["ssim"] - 1.0) < 1e-5              # identical images
     for thr in ("0.50", "2.00", "4.00", "8.00"):
         assert abs(m[f"cat_thr{thr}/pod"] - 1.0) < 1e-6 and m[f"cat_thr{thr}/far"] == 0.0
         for s in (1, 2, 4, 8):
@@ -67,3 +68,23 @@ def test_metric_suite_stress_256_and_properties():
         assert float(st[3 + 4 * t:7 + 4 * t].sum()) == 8 * 20 * 256 * 256
     with pytest.raises(ValueError):
         RainfallMetricSuite(MetricConfig(scales=(1, 3)))
+
+
+def test_ssim_matches_oracle_restatement_and_small_images():
+    """SSIM vs the oracle's restatement of torchmetrics' algorithm (parity unpinned: torchmetrics is absent), on raw and
+    transformed values, ragged sizes; images not larger than the 11x11 window report NaN."""
+    from p2igan_b200.metrics import MetricConfig, RainfallMetricSuite
+    g = torch.Generator().manual_seed(8)
+    for shape, tr, scale in (((3, 4, 1, 37, 53), False, 1.0), ((2, 16, 1, 128, 128), True, 60.0), ((1, 2, 1, 11, 30), False, 1.0)):
+        pred = torch.rand(shape, generator=g) * scale
+        tgt = (pred + 0.2 * scale * torch.rand(shape, generator=g)).clamp(0, scale)
+        suite = RainfallMetricSuite(MetricConfig(apply_transform=tr)).to(DEV)
+        suite.update(pred.to(DEV), tgt.to(DEV))
+        got = suite.compute()["ssim"]
+        H, W = shape[-2:]
+        p, t = (O.rain_rate(pred), O.rain_rate(tgt)) if tr else (pred, tgt)
+        ref = float(O.ssim_per_image(p.reshape(-1, 1, H, W), t.reshape(-1, 1, H, W)).mean())
+        assert abs(got - ref) < 1e-3, (shape, got, ref)
+    small = RainfallMetricSuite(MetricConfig()).to(DEV)
+    small.update(torch.rand(1, 2, 1, 8, 8).to(DEV), torch.rand(1, 2, 1, 8, 8).to(DEV))
+    assert math.isnan(small.compute()["ssim"])
