@@ -10,7 +10,11 @@ Pinning: the reference ships no tests or golden vectors, s
 pinned against outputs of the reference itself, executed in the build container by
 ``tests/golden/make_golden.py`` (imports /root/reference with an in-memory torchmetrics stub) and
 committed under ``tests/golden/``.  ``tests/test_oracle_golden.py`` checks every function below
-against those vectors.
+against those vectors; ``batch_post_process`` is pinned by ``tests/golden/make_golden_data.py`` (the reference's own
+``Dataset.post_process``) and ``tests/test_batch_prep_oracle.py``.
+PARITY UNPINNED for exactly one function: ``ssim_per_image`` restates torchmetrics 1.0.3 (a third-party dependency of
+the reference, pinned in its uv.lock:1162-1164, absent from /root/reference and from this image) from its published
+algorithm; the reference holds no SSIM value to check it against.
 
 Everything is functional: parameters come in as a ``state_dict``-style mapping with the
 reference's key names, so the same weights can be fed to the CUDA modules and to the oracle.
@@ -31,6 +35,8 @@ Reference citations (file:line under /root/reference):
   metrics                   p2igan_bench/metrics/metric.py:16-183
   train step order          scripts/train.py:240-326
   sliding-window inference  scripts/infer.py:217-245
+  batch preparation         p2igan_bench/data/sti_dataset.py:203-243, scripts/train.py:468-473
+  SSIM                      p2igan_bench/metrics/metric.py:36,55-56,69 -> torchmetrics (unpinned, see above)
 """
 from __future__ import annotations
 
