@@ -301,6 +301,11 @@ __global__ void __launch_bounds__(128) d3d_first_fwd4_kernel(const float* __rest
     }
 }
 
+
+// (A warp-MMA variant -- im2col fragments gathered from a staged patch, 8 mma.sync.m16n8k16 per 16 pixels -- was built and
+// measured at 108 us against 78 us for the kernel above: 618 instructions per 16-pixel tile and only 20 resident warps
+// left it bound by the global-load latency of the patch; it was dropped.)
+
 // ------------------------------------------------------------------------------------------------
 // d2d.8: Conv2d(256 -> 1, 3x3, pad 1) + bias, no activation.  y bf16 [B,H,W,C]; w f32 [C][9] (weight_orig),
 // out f32 [B,H,W].  One warp per output pixel, lanes over channels (8 per lane per 256).

@@ -102,7 +102,7 @@ namespace p2i {
 // channels): per output channel the warp loads the 288 contiguous weights and read-modify-writes the 288 contiguous
 // dW values through a per-warp staging buffer (coalesced), keeps the 9x9 dD partial of its input channel in
 // registers, and the block reduces the 8 warps in turn before one global atomic per element.
-__global__ void __launch_bounds__(256) doconv_bwd_kernel(const P2iDoGrad* __restrict__ table) {
+__global__ void __launch_bounds__(256, 2) doconv_bwd_kernel(const P2iDoGrad* __restrict__ table) {
     const P2iDoGrad L = table[blockIdx.z];
     const int C = L.channels;
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
@@ -125,11 +125,16 @@ __global__ void __launch_bounds__(256) doconv_bwd_kernel(const P2iDoGrad* __rest
     for (int q = 0; q < 8; ++q) {
         const int o = o0 + oo + 8 * q;
         const size_t rowoff = (static_cast<size_t>(o) * C + i0) * 9;
-        float g[9], w[9];
+        // all 27 global loads of this output channel (gradient, weights, old dW) are issued before anything waits
+        float g[9], w[9], wst[9], dwo[9];
 #pragma unroll
         for (int m = 0; m < 9; ++m) g[m] = __ldg(L.dDoW + (static_cast<size_t>(m) * C + o) * C + i);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sW[oo][ii + 32 * k] = __ldg(L.W + rowoff + ii + 32 * k);
+        for (int k = 0; k < 9; ++k) wst[k] = __ldg(L.W + rowoff + ii + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dwo[k] = L.dW[rowoff + ii + 32 * k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sW[oo][ii + 32 * k] = wst[k];
         __syncwarp();
 #pragma unroll
         for (int s9 = 0; s9 < 9; ++s9) w[s9] = sW[oo][ii * 9 + s9];
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(256) doconv_bwd_kernel(const P2iDoGrad* __rest
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 9; ++k) L.dW[rowoff + ii + 32 * k] += sW[oo][ii + 32 * k];
+        for (int k = 0; k < 9; ++k) L.dW[rowoff + ii + 32 * k] = dwo[k] + sW[oo][ii + 32 * k];
         __syncwarp();
     }
     for (int wv = 0; wv < 8; ++wv) {
