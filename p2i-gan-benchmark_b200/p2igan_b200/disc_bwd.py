@@ -102,42 +102,55 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
              ptr(mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(d_o2d), ptr(tg.get("alpha2d")),
              ptr(dpre_z4), ptr(G.get("d3d.8")), ptr(dbias.get("d3d.8")), B, T2, h8, w8, 128, h4, w4, stream())
 
-    # ---- d2d.8
-    dpre_y4 = torch.empty_like(ctx["y4"])
-    LIB.call("p2i_d2d_last_bwd", ptr(d_o2d), ptr(ctx["y4"]), ptr(mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")),
-             ptr(dpre_y4), ptr(G.get("d2d.8")), ptr(dbias.get("d2d.8")), B, h4, w4, 256, stream())
-
-    def tc_layer(name, x_in, dpre, fdesc, ddesc, mask, out_shape):
+    def tc_layer(name, x_in, dpre, fdesc, ddesc, mask, out):
         """wgrad + bias grad (if needed) and dgrad of one tensor-core layer -> d(pre-activation) of the layer below."""
         if need_params:
+            # the bias gradient (HBM-bound column sum of dpre) goes to the aux stream, next to this layer's wgrad / dgrad GEMMs
+            cur = torch.cuda.current_stream()
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                _colsum(dpre, dbias[name])
             conv_wgrad(x_in, dpre, G[name], fdesc)
-            _colsum(dpre, dbias[name])
         if ddesc is None:
             return None
-        out = torch.empty(out_shape, dtype=bf, device=dev)
         conv_igemm(dpre, wt[name], ddesc, mask=mask, out=out)
         return out
 
-    # ---- 2-D branch (top-down)
-    d = tc_layer("d2d.6", ctx["y3"], dpre_y4, conv_desc(B, 1, 1, h4, w4, 256, 256, 1, 3, 1, 0),
-                 conv_desc(B, 1, 1, h4, w4, 256, 256, 1, 3, 1, 0, mask_mode=2), ctx["y3"], ctx["y3"].shape)
-    d = tc_layer("d2d.4", ctx["y2"], d, conv_desc(B, 1, 1, h4, w4, 512, 256, 1, 2, 1, 0),
-                 conv_desc(B, 1, 1, h4, w4, 256, 512, 1, 2, 0, 0, mask_mode=2, out_mode=2), ctx["y2"], (B, H // 2, W // 2, 128))
-    d = tc_layer("d2d.2", ctx["y1"], d, conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0),
-                 conv_desc(B, 1, 1, H // 2, W // 2, 128, 256, 1, 2, 0, 0, mask_mode=2, out_mode=2), ctx["y1"], (B, H, W, 64))
-    d_a0 = tc_layer("d2d.0", ctx["a0"], d, conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0),
-                    conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0) if need_input else None, None, (B, H, W, 64))
-
-    # ---- 3-D branch (top-down)
-    d = tc_layer("d3d.6", ctx["z3"], dpre_z4, conv_desc(B, T, T2, h8, w8, 128, 128, 3, 3, 1, 1, stride_t=2),
-                 conv_desc(B, T2, T, h8, w8, 128, 128, 3, 3, 1, 1, stride_t=2, t_transposed=1, mask_mode=2), ctx["z3"], ctx["z3"].shape)
-    d = tc_layer("d3d.4", ctx["z2"], d, conv_desc(B, T, T, h8, w8, 256, 128, 3, 2, 1, 1),
-                 conv_desc(B, T, T, h8, w8, 128, 256, 3, 2, 0, 1, mask_mode=2, out_mode=2), ctx["z2"], (B, T, h4, w4, 64))
-    d = tc_layer("d3d.2", ctx["z1"], d, conv_desc(B, T, T, h4, w4, 128, 64, 3, 2, 1, 1),
-                 conv_desc(B, T, T, h4, w4, 64, 128, 3, 2, 0, 1, mask_mode=2, out_mode=2), ctx["z1"], (B, T, H // 2, W // 2, 32))
+    # buffers of both branches are allocated on the main stream before the fork (per-stream caching allocator)
+    dpre_y4 = torch.empty_like(ctx["y4"])
+    e2 = [torch.empty_like(ctx["y3"]), torch.empty(B, H // 2, W // 2, 128, dtype=bf, device=dev), torch.empty(B, H, W, 64, dtype=bf, device=dev),
+          torch.empty(B, H, W, 64, dtype=bf, device=dev) if need_input else None]
+    e3 = [torch.empty_like(ctx["z3"]), torch.empty(B, T, h4, w4, 64, dtype=bf, device=dev), torch.empty(B, T, H // 2, W // 2, 32, dtype=bf, device=dev)]
     dx = torch.empty(B, T, H, W, dtype=f32, device=dev) if need_input else None
-    LIB.call("p2i_d3d_first_bwd", ptr(d), ptr(ctx["xf"]), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")),
-             ptr(G.get("d3d.0")), ptr(dbias.get("d3d.0")), ptr(dx), B, T, H, W, stream())
+    main = torch.cuda.current_stream()
+    side, aux = state.side, state.aux
+    side.wait_stream(main)
+
+    # ---- 3-D branch (top-down) on the side stream: its CUDA-core first-layer kernels overlap the 2-D branch's GEMMs
+    with torch.cuda.stream(side):
+        d = tc_layer("d3d.6", ctx["z3"], dpre_z4, conv_desc(B, T, T2, h8, w8, 128, 128, 3, 3, 1, 1, stride_t=2),
+                     conv_desc(B, T2, T, h8, w8, 128, 128, 3, 3, 1, 1, stride_t=2, t_transposed=1, mask_mode=2), ctx["z3"], e3[0])
+        d = tc_layer("d3d.4", ctx["z2"], d, conv_desc(B, T, T, h8, w8, 256, 128, 3, 2, 1, 1),
+                     conv_desc(B, T, T, h8, w8, 128, 256, 3, 2, 0, 1, mask_mode=2, out_mode=2), ctx["z2"], e3[1])
+        d = tc_layer("d3d.2", ctx["z1"], d, conv_desc(B, T, T, h4, w4, 128, 64, 3, 2, 1, 1),
+                     conv_desc(B, T, T, h4, w4, 64, 128, 3, 2, 0, 1, mask_mode=2, out_mode=2), ctx["z1"], e3[2])
+        LIB.call("p2i_d3d_first_bwd", ptr(d), ptr(ctx["xf"]), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")),
+                 ptr(G.get("d3d.0")), ptr(dbias.get("d3d.0")), ptr(dx), B, T, H, W, stream())
+
+    # ---- d2d.8 and the 2-D branch (top-down) on the main stream
+    LIB.call("p2i_d2d_last_bwd", ptr(d_o2d), ptr(ctx["y4"]), ptr(mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")),
+             ptr(dpre_y4), ptr(G.get("d2d.8")), ptr(dbias.get("d2d.8")), B, h4, w4, 256, stream())
+    d = tc_layer("d2d.6", ctx["y3"], dpre_y4, conv_desc(B, 1, 1, h4, w4, 256, 256, 1, 3, 1, 0),
+                 conv_desc(B, 1, 1, h4, w4, 256, 256, 1, 3, 1, 0, mask_mode=2), ctx["y3"], e2[0])
+    d = tc_layer("d2d.4", ctx["y2"], d, conv_desc(B, 1, 1, h4, w4, 512, 256, 1, 2, 1, 0),
+                 conv_desc(B, 1, 1, h4, w4, 256, 512, 1, 2, 0, 0, mask_mode=2, out_mode=2), ctx["y2"], e2[1])
+    d = tc_layer("d2d.2", ctx["y1"], d, conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0),
+                 conv_desc(B, 1, 1, H // 2, W // 2, 128, 256, 1, 2, 0, 0, mask_mode=2, out_mode=2), ctx["y1"], e2[2])
+    d_a0 = tc_layer("d2d.0", ctx["a0"], d, conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0),
+                    conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0) if need_input else None, None, e2[3])
+    main.wait_stream(side)
+    if need_params:                 # aux was forked in this call (joining a stream that is not part of a capture is an error)
+        main.wait_stream(aux)
     if need_input:
         LIB.call("p2i_disc_unpack_input_grad", ptr(d_a0), ptr(dx), B, 16, H, W, stream())
         dx = dx.view(B, T, 1, H, W)

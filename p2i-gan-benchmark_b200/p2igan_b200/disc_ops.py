@@ -110,6 +110,10 @@ class DiscState:
         self.key = tuple(m.weight_orig.data_ptr() for m in self.mods.values())
         self.sets = [_OperandSet(self.mods, self.dev) for _ in range(N_SETS)]
         self.calls = 0
+        # the 3-D branch runs on a side stream next to the 2-D branch (fork / join with events; CUDA-graph capturable): its
+        # thin CUDA-core first layer then overlaps the 2-D branch's tensor-core kernels instead of queueing behind them
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.aux = torch.cuda.Stream(device=self.dev)      # bias column-sums of the backward pass
 
     def next_set(self) -> _OperandSet:
         s = self.sets[self.calls % N_SETS]
@@ -144,31 +148,37 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     LIB.call("p2i_disc_pack_weights", ptr(st.pack_table), len(TC_LAYERS), stream())
     bf = torch.bfloat16
     bias = {n: mods[n].bias.detach() for n in ALL_SN}
-    # ---- 2-D branch
+    # every buffer is allocated on the main stream BEFORE the fork (the caching allocator is per stream)
     a0 = torch.empty(B, H, W, 64, dtype=bf, device=dev)
-    LIB.call("p2i_disc_pack_input", ptr(xf), ptr(a0), B, 16, H, W, stream())
     y1 = torch.empty(B, H // 2, W // 2, 256, dtype=bf, device=dev)
-    conv_igemm(a0, st.w["d2d.0"], conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0, act=2, out_mode=1), bias=bias["d2d.0"], out=y1)
     y2 = torch.empty(B, H // 4, W // 4, 512, dtype=bf, device=dev)
-    conv_igemm(y1, st.w["d2d.2"], conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0, act=2, out_mode=1), bias=bias["d2d.2"], out=y2)
     y3 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
-    conv_igemm(y2, st.w["d2d.4"], conv_desc(B, 1, 1, H // 4, W // 4, 512, 256, 1, 2, 1, 0, act=2), bias=bias["d2d.4"], out=y3)
     y4 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
-    conv_igemm(y3, st.w["d2d.6"], conv_desc(B, 1, 1, H // 4, W // 4, 256, 256, 1, 3, 1, 0, act=2), bias=bias["d2d.6"], out=y4)
     o2d = torch.empty(B, H // 4, W // 4, dtype=torch.float32, device=dev)
+    T2 = (T + 2 - 3) // 2 + 1
+    z1 = torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev)
+    z2 = torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev)
+    z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
+    z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
+    main = torch.cuda.current_stream()
+    side = state.side
+    side.wait_stream(main)
+    # ---- 3-D branch (side stream)
+    with torch.cuda.stream(side):
+        LIB.call("p2i_d3d_first_fwd", ptr(xf), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")), ptr(bias["d3d.0"]),
+                 ptr(z1), B, T, H, W, stream())
+        conv_igemm(z1, st.w["d3d.2"], conv_desc(B, T, T, H // 4, W // 4, 128, 64, 3, 2, 1, 1, act=2, out_mode=1), bias=bias["d3d.2"], out=z2)
+        conv_igemm(z2, st.w["d3d.4"], conv_desc(B, T, T, H // 8, W // 8, 256, 128, 3, 2, 1, 1, act=2), bias=bias["d3d.4"], out=z3)
+        conv_igemm(z3, st.w["d3d.6"], conv_desc(B, T, T2, H // 8, W // 8, 128, 128, 3, 3, 1, 1, stride_t=2, act=2), bias=bias["d3d.6"], out=z4)
+    # ---- 2-D branch (main stream)
+    LIB.call("p2i_disc_pack_input", ptr(xf), ptr(a0), B, 16, H, W, stream())
+    conv_igemm(a0, st.w["d2d.0"], conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0, act=2, out_mode=1), bias=bias["d2d.0"], out=y1)
+    conv_igemm(y1, st.w["d2d.2"], conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0, act=2, out_mode=1), bias=bias["d2d.2"], out=y2)
+    conv_igemm(y2, st.w["d2d.4"], conv_desc(B, 1, 1, H // 4, W // 4, 512, 256, 1, 2, 1, 0, act=2), bias=bias["d2d.4"], out=y3)
+    conv_igemm(y3, st.w["d2d.6"], conv_desc(B, 1, 1, H // 4, W // 4, 256, 256, 1, 3, 1, 0, act=2), bias=bias["d2d.6"], out=y4)
     LIB.call("p2i_d2d_last_fwd", ptr(y4), ptr(mods["d2d.8"].weight_orig.detach()), ptr(st.sig("d2d.8")), ptr(bias["d2d.8"]),
              ptr(o2d), B, H // 4, W // 4, 256, stream())
-    # ---- 3-D branch
-    z1 = torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev)
-    LIB.call("p2i_d3d_first_fwd", ptr(xf), ptr(mods["d3d.0"].weight_orig.detach()), ptr(st.sig("d3d.0")), ptr(bias["d3d.0"]),
-             ptr(z1), B, T, H, W, stream())
-    z2 = torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev)
-    conv_igemm(z1, st.w["d3d.2"], conv_desc(B, T, T, H // 4, W // 4, 128, 64, 3, 2, 1, 1, act=2, out_mode=1), bias=bias["d3d.2"], out=z2)
-    z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
-    conv_igemm(z2, st.w["d3d.4"], conv_desc(B, T, T, H // 8, W // 8, 256, 128, 3, 2, 1, 1, act=2), bias=bias["d3d.4"], out=z3)
-    T2 = (T + 2 - 3) // 2 + 1
-    z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
-    conv_igemm(z3, st.w["d3d.6"], conv_desc(B, T, T2, H // 8, W // 8, 128, 128, 3, 3, 1, 1, stride_t=2, act=2), bias=bias["d3d.6"], out=z4)
+    main.wait_stream(side)
     # ---- tail
     m = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev)
     fused = torch.empty(B, (H // 4) * (W // 4), dtype=torch.float32, device=dev)

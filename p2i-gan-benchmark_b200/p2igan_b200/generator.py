@@ -145,11 +145,23 @@ class P2IGenerator(BaseNetwork):
             self._gtable = gt
         return gt
 
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        st = getattr(self, "_side", None)
+        if st is None or st.device != torch.device(device):
+            st = torch.cuda.Stream(device=device)
+            self._side = st
+        return st
+
     def _forward_train(self, mf, mk):
         """Forward that keeps what the backward needs. Returns (out f32 [B,16,H,W], saved dict)."""
+        # the InputBlock (latency-bound CUDA-core kernels) runs on a side stream next to the weight composition
+        main, side = torch.cuda.current_stream(), self._side_stream(mf.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            x_in, ictx = self.input.forward_ctx(mf, mk, save_for_backward=True)
         wc = self._weights(need_dgrad=True)
         bufs = wc["bufs"]
-        x_in, ictx = self.input.forward_ctx(mf, mk, save_for_backward=True)
+        main.wait_stream(side)
         sv = {"ictx": ictx, "x_in": x_in, "wc": wc, "res": {}, "up": {}}
 
         def eblock(level, x):
@@ -236,6 +248,20 @@ class P2IGenerator(BaseNetwork):
         d_x4 = d
         d = up_bwd(2, d)
         d_x8 = eblock_bwd(3, d)
+        # every weight gradient of the 32 DO-Conv layers is in the arena now: their composition backward (HBM-bound) runs on a
+        # side stream next to the stem / InputBlock backward chain (CUDA-core, latency-bound)
+        main, side = torch.cuda.current_stream(), self._side_stream(dout.device)
+        convs = list(self._res_convs())
+        names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
+        key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
+        if gt.get("bwd_key") != key:
+            tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), tg[n + ".W"].data_ptr(),
+                                       tg[n + ".D"].data_ptr(), c.in_channels) for (_, c), g, n in zip(convs, gviews, names)])
+            gt["bwd_table"] = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
+            gt["bwd_key"] = key
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.doconv_compose_bwd(gt["bwd_table"], len(convs), max(c.in_channels for _, c in convs))
         d_stem = ops.pyramid_bwd(sv["stem"], d_x4, d_x8)
         dx_in, dw_stem = ops.stem_bwd(d_stem, sv["x_in"], wc["stem"])
         s = self.Convsin[0].main[0]
@@ -247,16 +273,7 @@ class P2IGenerator(BaseNetwork):
         w0, b0, w1, b1 = (p.detach().contiguous() for p in self.input.gate_params())
         ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals, tg["input.layers.0.conv.weight"],
                             tg["input.layers.0.conv.bias"], tg["input.layers.1.conv.weight"], tg["input.layers.1.conv.bias"])
-        # DO-Conv composition backward for the 32 ResBlock convs (one batched launch pair); the device table is cached
-        convs = list(self._res_convs())
-        names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
-        key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
-        if gt.get("bwd_key") != key:
-            tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), tg[n + ".W"].data_ptr(),
-                                       tg[n + ".D"].data_ptr(), c.in_channels) for (_, c), g, n in zip(convs, gviews, names)])
-            gt["bwd_table"] = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
-            gt["bwd_key"] = key
-        ops.doconv_compose_bwd(gt["bwd_table"], len(convs), max(c.in_channels for _, c in convs))
+        main.wait_stream(side)
         return fresh
 
 
