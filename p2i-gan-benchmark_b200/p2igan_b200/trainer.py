@@ -26,7 +26,7 @@ LOSS_KEYS = ("rec", "pool", "reg", "adv", "dis", "total")
 
 class Trainer:
     def __init__(self, cfg: Dict[str, Any], device: Optional[torch.device] = None, process_group=None, use_graphs: bool = True,
-                 log_fn: Optional[Callable[[int, Dict[str, float]], None]] = None):
+                 log_fn: Optional[Callable[[int, Dict[str, float]], None]] = None, peer_exchange: bool = True):
         self.cfg = cfg
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         torch.manual_seed(cfg.get("seed", 42))
@@ -36,7 +36,8 @@ class Trainer:
         self.generator.train()
         if self.discriminator is not None:
             self.discriminator.train()
-        self.ts = GANTrainStep(cfg, self.generator, self.discriminator, process_group=process_group)
+        # multi-GPU: NVLink peer-memory gradient exchange (one graph per step) unless peer_exchange=False (NCCL, three graphs)
+        self.ts = GANTrainStep(cfg, self.generator, self.discriminator, process_group=process_group, peer_exchange=peer_exchange)
         self.opt_g, self.opt_d = self.ts.opt_g, self.ts.opt_d
         self.rec_loss = ReconstructionLoss(k1_alpha=cfg["loss"].get("k1_weight", 0.0))
         train_cfg = cfg.get("train", {})
@@ -69,7 +70,7 @@ class Trainer:
                 return self.ts.step(frames, masked, masks)
             # capture executes nothing: the first replay below IS this batch's training step
             world = torch.distributed.get_world_size(self.ts.pg) if torch.distributed.is_initialized() else 1
-            if world > 1:
+            if world > 1 and not self.ts.peer_exchange:
                 self._graphed = GraphedDPStep(self.ts, (frames, masked, masks), warmup=0)
             else:
                 self._graphed = GraphedStep(lambda a, b, c: self.ts.step(a, b, c), (frames, masked, masks), warmup=0)
