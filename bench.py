@@ -167,8 +167,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_events = 2
-    steps, warmup = max(1, min(args.steps, 3)), 1
+    n_events = 4
+    steps, warmup = max(1, min(args.steps, 6)), 1          # bounded sample: ~10-20 s of CPU work on the box's host cores
     fn = cpu_train_events_per_s if args.workload == "train" else cpu_generator_events_per_s
     v, cores, spp = fn(n_events, steps, warmup)
     metric, wl = WORKLOADS[args.workload]
@@ -476,10 +476,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             fn = cpu_train_events_per_s if train else cpu_generator_events_per_s
-            v, cores, spp = fn(2, 2, 1)
+            v, cores, spp = fn(4, 5, 1)
             line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                                    "sample": "2 events/step x 2 steps of the same workload (oracle/p2i_oracle.py, torch CPU fp32 "
-                                              "restatement of the reference, reference-style IDW)"}
+                                    "sample": "4 events/step x 5 timed steps (+1 warm-up) of the same workload (oracle/p2i_oracle.py, torch "
+                                              "CPU fp32 restatement of the reference, reference-style IDW)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
