@@ -9,6 +9,7 @@ semantics: validation loss, reference-format checkpoints, resume) and ``prepare_
 Every op is a hand-written CUDA kernel in ``libp2i_sm100a.so`` (C ABI: include/p2i_b200.h);
 there is no CPU, PyTorch-eager or Triton fallback.
 """
+from ._overlap import set_stream_overlap  # noqa: F401
 from .data import prepare_batch, prepare_batch_u8  # noqa: F401
 from .discriminator import P2IDiscriminator  # noqa: F401
 from .generator import P2IGenerator  # noqa: F401
@@ -22,4 +23,4 @@ from .trainer import Trainer  # noqa: F401
 
 __all__ = ["P2IGenerator", "P2IDiscriminator", "build_generator", "build_discriminator", "ReconstructionLoss", "gan_loss",
            "MetricConfig", "RainfallMetricSuite", "transform", "FusedAdam", "GANTrainStep", "GraphedStep", "FlatGrads",
-           "GraphedDPStep", "sliding_window_infer", "Trainer", "prepare_batch", "prepare_batch_u8"]
+           "GraphedDPStep", "sliding_window_infer", "Trainer", "prepare_batch", "prepare_batch_u8", "set_stream_overlap"]

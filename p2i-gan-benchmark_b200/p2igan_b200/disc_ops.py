@@ -19,6 +19,7 @@ from typing import Dict, List, Optional
 
 import torch
 
+from . import _overlap
 from ._lib import LIB, ptr, require_cuda, stream
 
 D2D = [0, 2, 4, 6, 8]
@@ -161,7 +162,7 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
     z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
     main = torch.cuda.current_stream()
-    side = state.side
+    side = _overlap.pick(state.side, main)
     side.wait_stream(main)
     # ---- 3-D branch (side stream)
     with torch.cuda.stream(side):

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import _overlap
 from ._lib import pack_do_grad_table, pack_do_table, require_cuda
 from .layers import (BaseNetwork, BasicConv_do, DownsampleDuplicateChannels, EBlock, InputBlock, ResBlock_do, UPPos)
 
@@ -155,7 +156,8 @@ class P2IGenerator(BaseNetwork):
     def _forward_train(self, mf, mk):
         """Forward that keeps what the backward needs. Returns (out f32 [B,16,H,W], saved dict)."""
         # the InputBlock (latency-bound CUDA-core kernels) runs on a side stream next to the weight composition
-        main, side = torch.cuda.current_stream(), self._side_stream(mf.device)
+        main = torch.cuda.current_stream()
+        side = _overlap.pick(self._side_stream(mf.device), main)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             x_in, ictx = self.input.forward_ctx(mf, mk, save_for_backward=True)
@@ -250,7 +252,8 @@ class P2IGenerator(BaseNetwork):
         d_x8 = eblock_bwd(3, d)
         # every weight gradient of the 32 DO-Conv layers is in the arena now: their composition backward (HBM-bound) runs on a
         # side stream next to the stem / InputBlock backward chain (CUDA-core, latency-bound)
-        main, side = torch.cuda.current_stream(), self._side_stream(dout.device)
+        main = torch.cuda.current_stream()
+        side = _overlap.pick(self._side_stream(dout.device), main)
         convs = list(self._res_convs())
         names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
         key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
