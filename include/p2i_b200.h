@@ -198,7 +198,8 @@ int p2i_upmod_bwd(const void* z, const float* pos, const float* bias, const void
 /* d(x4) [B,H/4,W/4,256], d(x8) [B,H/8,W/8,512] -> d(stem) [B,H,W,64] bf16 (overwritten), routed to the arg-max
  * pixels of the saved stem output (max_pool2d backward + repeat_interleave backward, layer.py:210-213). */
 int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx8, void* dstem, int B, int H, int W, void* stream);
-/* dy [B,H,W,64] bf16, x f32 [B,16,H,W], w f32 [64,4,9] -> dx f32 [B,16,H,W] (overwritten), dw f32 [64,4,9] accumulated. */
+/* dy [B,H,W,64] bf16, x f32 [B,16,H,W], w f32 [64,4,9] -> dx f32 [B,16,H,W] (overwritten), dw f32 [64,4,9] accumulated.
+ * dx or dw may be NULL: only the other gradient is computed (two independent kernels). */
 int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

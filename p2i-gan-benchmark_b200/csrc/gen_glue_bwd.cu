@@ -428,46 +428,6 @@ __global__ void __launch_bounds__(256) stem_bwd_dw2_kernel(const __nv_bfloat16* 
         if (acc[k] != 0.f) atomicAdd(&dw[(oc * 4 + icl) * 9 + k], acc[k]);
 }
 
-// thread = (pixel sub-stream s in 0..3, group g, output quad oq, input channel icl): 4 oc x 9 taps accumulators.
-__global__ void __launch_bounds__(256) stem_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
-                                                          float* __restrict__ dw, int B, int H, int W) {
-    __shared__ float sdw[64 * 36];
-    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sdw[i] = 0.f;
-    __syncthreads();
-    const int t = threadIdx.x;
-    const int icl = t & 3, oq = (t >> 2) & 3, g = (t >> 4) & 3, s = t >> 6;
-    const size_t HW = static_cast<size_t>(H) * W;
-    float acc[4][9];
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[o][k] = 0.f;
-    const long long npix = static_cast<long long>(B) * HW;
-    for (long long p = static_cast<long long>(blockIdx.x) * 4 + s; p < npix; p += static_cast<long long>(gridDim.x) * 4) {
-        const int b = static_cast<int>(p / HW);
-        const int pix = static_cast<int>(p - b * HW), yy = pix / W, xx = pix - yy * W;
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(dy + p * 64 + g * 16 + oq * 4));
-        const float2 d01 = unpack_bf16x2(q.x), d23 = unpack_bf16x2(q.y);
-        const float d[4] = {d01.x, d01.y, d23.x, d23.y};
-        const float* xb = x + (static_cast<size_t>(b) * 16 + g * 4 + icl) * HW;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int iy = yy + ky - 1, ix = xx + kx - 1;
-                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + static_cast<size_t>(iy) * W + ix) : 0.f;
-#pragma unroll
-                for (int o = 0; o < 4; ++o) acc[o][ky * 3 + kx] = fmaf(d[o], v, acc[o][ky * 3 + kx]);
-            }
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) atomicAdd(&sdw[((g * 16 + oq * 4 + o) * 4 + icl) * 9 + k], acc[o][k]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) atomicAdd(&dw[i], sdw[i]);
-}
-
 }  // namespace p2i
 
 using namespace p2i;
@@ -516,14 +476,18 @@ extern "C" int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx
 
 extern "C" int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W,
                             void* stream) {
-    P2I_CHECK_ARG(dy && x && w && dx && dw, "stem_bwd: null pointer");
-    dim3 grid(cdiv(W, 32), cdiv(H, 4), B);
-    stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
-    P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");
-    long long tiles = static_cast<long long>(B) * H * ((W + 63) / 64);
-    P2I_CHECK_ARG(tiles < (1ll << 31), "stem_bwd: tensor too large");
-    if (tiles > sm_count() * 4) tiles = sm_count() * 4;
-    stem_bwd_dw2_kernel<<<static_cast<unsigned>(tiles), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
-    P2I_CHECK_LAUNCH("stem_bwd_dw2_kernel");
+    P2I_CHECK_ARG(dy && x && w && (dx || dw), "stem_bwd: null pointer");
+    if (dx) {        // dx == NULL / dw == NULL: only the other gradient (the two kernels are independent; callers may run them on two streams)
+        dim3 grid(cdiv(W, 32), cdiv(H, 4), B);
+        stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
+        P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");
+    }
+    if (dw) {
+        long long tiles = static_cast<long long>(B) * H * ((W + 63) / 64);
+        P2I_CHECK_ARG(tiles < (1ll << 31), "stem_bwd: tensor too large");
+        if (tiles > sm_count() * 4) tiles = sm_count() * 4;
+        stem_bwd_dw2_kernel<<<static_cast<unsigned>(tiles), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), x, dw, B, H, W);
+        P2I_CHECK_LAUNCH("stem_bwd_dw2_kernel");
+    }
     return P2I_OK;
 }

@@ -350,3 +350,22 @@ def test_train_step_256_stress_and_one_percent_gauges():
     ref = 0.5 * (g0 + g1)
     rel = float((g01 - ref).norm() / ref.norm())
     assert rel < 2e-2, rel            # bf16 activations: the two paths round differently, fp32 would give ~1e-6
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,k", [(64, 64, 32, 32, 3), (64, 64, 24, 40, 3), (128, 128, 16, 16, 3), (256, 128, 16, 16, 1)])
+def test_experimental_wgrad_variants_match_first_generation(Cin, Cout, H, W, k):
+    """p2i_set_wgrad_impl(2): the all-taps (64->64) and flipped-GEMM kernels kept for A/B runs must stay correct."""
+    from p2igan_b200._lib import LIB
+    from p2igan_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(2, H, W, Cin, device=DEV, generator=g).to(torch.bfloat16)
+    dy = torch.randn(2, H, W, Cout, device=DEV, generator=g).to(torch.bfloat16)
+    try:
+        LIB.call("p2i_set_wgrad_impl", 1)
+        a = ops.conv2d_wgrad(x, dy, k)
+        LIB.call("p2i_set_wgrad_impl", 2)
+        b = ops.conv2d_wgrad(x, dy, k)
+    finally:
+        LIB.call("p2i_set_wgrad_impl", 0)
+    torch.cuda.synchronize()
+    assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-4
