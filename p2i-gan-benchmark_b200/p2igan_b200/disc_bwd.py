@@ -124,7 +124,7 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
     e3 = [torch.empty_like(ctx["z3"]), torch.empty(B, T, h4, w4, 64, dtype=bf, device=dev), torch.empty(B, T, H // 2, W // 2, 32, dtype=bf, device=dev)]
     dx = torch.empty(B, T, H, W, dtype=f32, device=dev) if need_input else None
     main = torch.cuda.current_stream()
-    side, aux = _overlap.pick(state.side, main), _overlap.pick(state.aux, main)
+    side, aux = _overlap.pick(state.side, main, _overlap.D_BRANCH), _overlap.pick(state.aux, main, _overlap.D_COLSUM)
     side.wait_stream(main)
 
     # ---- 3-D branch (top-down) on the side stream: its CUDA-core first-layer kernels overlap the 2-D branch's GEMMs

@@ -162,7 +162,7 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
     z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
     z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
     main = torch.cuda.current_stream()
-    side = _overlap.pick(state.side, main)
+    side = _overlap.pick(state.side, main, _overlap.D_BRANCH)
     side.wait_stream(main)
     # ---- 3-D branch (side stream)
     with torch.cuda.stream(side):

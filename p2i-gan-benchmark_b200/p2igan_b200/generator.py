@@ -159,7 +159,7 @@ class P2IGenerator(BaseNetwork):
         """Forward that keeps what the backward needs. Returns (out f32 [B,16,H,W], saved dict)."""
         # the InputBlock (latency-bound CUDA-core kernels) runs on a side stream next to the weight composition
         main = torch.cuda.current_stream()
-        side = _overlap.pick(self._side_stream(mf.device), main)
+        side = _overlap.pick(self._side_stream(mf.device), main, _overlap.G_INPUT)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             x_in, ictx = self.input.forward_ctx(mf, mk, save_for_backward=True)
@@ -255,7 +255,7 @@ class P2IGenerator(BaseNetwork):
         # every weight gradient of the 32 DO-Conv layers is in the arena now: their composition backward (HBM-bound) runs on a
         # side stream next to the stem / InputBlock backward chain (CUDA-core, latency-bound)
         main = torch.cuda.current_stream()
-        side = _overlap.pick(self._side_stream(dout.device), main)
+        side = _overlap.pick(self._side_stream(dout.device), main, _overlap.G_DOCONV)
         convs = list(self._res_convs())
         names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
         key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
