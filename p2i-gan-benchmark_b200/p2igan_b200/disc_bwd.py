@@ -111,7 +111,9 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
             aux.wait_stream(cur)
             with torch.cuda.stream(aux):
                 _colsum(dpre, dbias[name])
-            conv_wgrad(x_in, dpre, G[name], fdesc)
+            waux.wait_stream(cur)
+            with torch.cuda.stream(waux):        # weight gradient: off the critical path (only the spectral-norm backward reads it)
+                conv_wgrad(x_in, dpre, G[name], fdesc)
         if ddesc is None:
             return None
         conv_igemm(dpre, wt[name], ddesc, mask=mask, out=out)
@@ -125,6 +127,7 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
     dx = torch.empty(B, T, H, W, dtype=f32, device=dev) if need_input else None
     main = torch.cuda.current_stream()
     side, aux = _overlap.pick(state.side, main, _overlap.D_BRANCH), _overlap.pick(state.aux, main, _overlap.D_COLSUM)
+    waux = _overlap.pick(state.aux, main, _overlap.D_WGRAD)
     side.wait_stream(main)
 
     # ---- 3-D branch (top-down) on the side stream: its CUDA-core first-layer kernels overlap the 2-D branch's GEMMs
@@ -152,6 +155,7 @@ def backward(D, ctx, dfused, need_params: bool, need_input: bool):
     main.wait_stream(side)
     if need_params:                 # aux was forked in this call (joining a stream that is not part of a capture is an error)
         main.wait_stream(aux)
+        main.wait_stream(waux)
     if need_input:
         LIB.call("p2i_disc_unpack_input_grad", ptr(d_a0), ptr(dx), B, 16, H, W, stream())
         dx = dx.view(B, T, 1, H, W)

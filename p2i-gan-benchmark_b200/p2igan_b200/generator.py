@@ -227,13 +227,27 @@ class P2IGenerator(BaseNetwork):
         d, dw_out = ops.head_bwd(dout.contiguous(), sv["out"], sv["r"], sv["w_out"])
         tg["ConvsOut.0.main.0.W"].add_(dw_out.reshape(16, 16, 1))
 
+        # Weight gradients are off the critical path (they only feed the arena): they run on the side stream while the
+        # data-gradient chain and the CUDA-core glue (UPPos / pyramid / stem / InputBlock backward) continue on the main
+        # stream.  Every tensor a side-stream kernel reads is kept alive in `keep` until the join (the caching allocator is
+        # per stream: a block freed on the main stream could otherwise be reused while the side stream still reads it).
+        main = torch.cuda.current_stream()
+        wside = _overlap.pick(self._side_stream(dout.device), main, _overlap.G_WGRAD)
+        keep = []
+
+        def wgrad_side(x, g, ks, out):
+            keep.extend((x, g))
+            wside.wait_stream(main)
+            with torch.cuda.stream(wside):
+                ops.conv2d_wgrad(x, g, ks, out=out)
+
         def eblock_bwd(level, d):
             base = level * 2 * self.num_res
             for r in reversed(range(self.num_res)):
                 a, y = sv["res"][level][r]
-                ops.conv2d_wgrad(y, d, 3, out=gviews[base + 2 * r + 1])
+                wgrad_side(y, d, 3, gviews[base + 2 * r + 1])
                 dy = ops.conv2d_cl(d, bufs_t[base + 2 * r + 1], None, False, mask=y)
-                ops.conv2d_wgrad(a, dy, 3, out=gviews[base + 2 * r])
+                wgrad_side(a, dy, 3, gviews[base + 2 * r])
                 d = ops.conv2d_cl(dy, bufs_t[base + 2 * r], d, False)
             return d
 
@@ -241,7 +255,7 @@ class P2IGenerator(BaseNetwork):
             x, z, pos, bias = sv["up"][i]
             dz = ops.upmod_bwd(z, pos, bias, d, tg[f"UP.{i}.proj.bias"], tg[f"UP.{i}.pos"])
             wv = tg[f"UP.{i}.proj.weight"]
-            ops.conv2d_wgrad(x, dz, 1, out=wv.view(1, wv.shape[0], wv.shape[1]))
+            wgrad_side(x, dz, 1, wv.view(1, wv.shape[0], wv.shape[1]))
             return ops.conv2d_cl(dz, wc["up_t"][i])
 
         d = eblock_bwd(0, d)
@@ -254,8 +268,9 @@ class P2IGenerator(BaseNetwork):
         d_x8 = eblock_bwd(3, d)
         # every weight gradient of the 32 DO-Conv layers is in the arena now: their composition backward (HBM-bound) runs on a
         # side stream next to the stem / InputBlock backward chain (CUDA-core, latency-bound)
-        main = torch.cuda.current_stream()
         side = _overlap.pick(self._side_stream(dout.device), main, _overlap.G_DOCONV)
+        if side is not wside:            # the composition backward must see the complete arena; on the same stream it is ordered already
+            main.wait_stream(wside)
         convs = list(self._res_convs())
         names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
         key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
