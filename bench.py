@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own messages (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -291,6 +294,8 @@ def run_ours(args):
         # single CUDA graph (p2igan_b200/peer.py); "nccl" = two NCCL all-reduces between three CUDA graphs
         exchange = os.environ.get("P2I_DP_EXCHANGE", "peer") if world > 1 else "none"
         ts = GANTrainStep(cfg, G, D, peer_exchange=(exchange == "peer"))
+        if world > 1 and exchange == "peer" and not ts.peer_exchange:
+            exchange = "nccl"            # CUDA IPC unavailable on this box: collective fallback (see GANTrainStep)
     else:
         G.eval()
         exchange = "none"

@@ -4,6 +4,7 @@ data-parallel training step is a single CUDA graph.  ``torch.distributed`` is on
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List
 
 import torch
@@ -42,22 +43,37 @@ class PeerBuffer:
             self.ptr = 0
 
 
-def _exchange(buf: PeerBuffer, group) -> List[int]:
-    """Pointers of every rank's buffer as mapped in this process (own entry = local pointer)."""
+def _exchange(buf: PeerBuffer, group):
+    """-> (pointers of every rank's buffer as mapped in this process (own entry = local pointer), error or None).
+    Never raises before all collectives of the exchange are done: a local failure is reported in the second value so
+    that the caller can take a COLLECTIVE decision (a rank that bailed out early would leave the others hanging)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    err = None
+    try:
+        mine = buf.handle()
+    except Exception as e:  # noqa: BLE001
+        mine, err = None, e
     handles = [None] * world
-    dist.all_gather_object(handles, buf.handle(), group=group)
+    dist.all_gather_object(handles, mine, group=group)
     ptrs = []
     for r in range(world):
         if r == rank:
             ptrs.append(buf.ptr)
             continue
-        q = ctypes.c_void_p()
-        h = ctypes.create_string_buffer(handles[r], 64)
-        LIB.call("p2i_peer_import", h, ctypes.byref(q))
-        buf._imported.append(q.value)
-        ptrs.append(q.value)
-    return ptrs
+        try:
+            if handles[r] is None:
+                raise RuntimeError(f"rank {r} could not export its buffer")
+            if os.environ.get("P2I_PEER_FAIL") == str(rank):          # test hook: simulate an IPC failure on one rank
+                raise RuntimeError("simulated CUDA IPC failure (P2I_PEER_FAIL)")
+            q = ctypes.c_void_p()
+            h = ctypes.create_string_buffer(handles[r], 64)
+            LIB.call("p2i_peer_import", h, ctypes.byref(q))
+            buf._imported.append(q.value)
+            ptrs.append(q.value)
+        except Exception as e:  # noqa: BLE001
+            err = err or e
+            ptrs.append(0)
+    return ptrs, err
 
 
 class PeerAllReduce:
@@ -74,10 +90,15 @@ class PeerAllReduce:
         self.buffer = PeerBuffer(self.n * 4, torch.float32)
         self.flags = PeerBuffer(int(LIB.load().p2i_peer_flags_bytes()), torch.int32)
         self.state = torch.zeros(2, dtype=torch.int32, device=self.buffer.tensor.device)     # [epoch, err]
-        bufs, flags = _exchange(self.buffer, group), _exchange(self.flags, group)
+        (bufs, e1), (flags, e2) = _exchange(self.buffer, group), _exchange(self.flags, group)
+        # collective verdict: either every rank mapped every buffer, or every rank raises here
+        ok = torch.tensor([0 if (e1 or e2) else 1], dtype=torch.int32, device=self.buffer.tensor.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0:
+            self.close()
+            raise RuntimeError(f"CUDA IPC peer mapping failed on at least one rank (local error: {e1 or e2!r})")
         self._bufs = (ctypes.c_void_p * self.world)(*bufs)
         self._flags = (ctypes.c_void_p * self.world)(*flags)
-        dist.barrier(group)             # every rank has mapped every buffer before the first kernel touches one
 
     @property
     def tensor(self) -> torch.Tensor:

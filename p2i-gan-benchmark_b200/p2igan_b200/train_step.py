@@ -78,13 +78,24 @@ class GANTrainStep:
         self.pg = process_group
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.peer_exchange = bool(peer_exchange and multi)
-        self.flat_g = FlatGrads(generator.parameters(), peer=self.peer_exchange, group=process_group)
+        d_params = [p for n, p in discriminator.named_parameters() if n != "alpha3d"] if self.use_gan else None
+        # alpha3d never receives a gradient in the reference (unused Parameter, models/p2igan.py:145): keep grad None
+        if self.peer_exchange:
+            # CUDA IPC can be unavailable (container policy, no P2P between the devices).  PeerAllReduce takes that decision
+            # collectively (it raises on every rank or on none), so all ranks fall back to the NCCL exchange together
+            try:
+                self.flat_g = FlatGrads(generator.parameters(), peer=True, group=process_group)
+                self.flat_d = FlatGrads(d_params, peer=True, group=process_group) if self.use_gan else None
+            except RuntimeError as e:
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({e}): using NCCL all-reduce")
+                self.peer_exchange = False
+        if not self.peer_exchange:
+            self.flat_g = FlatGrads(generator.parameters())
+            self.flat_d = FlatGrads(d_params) if self.use_gan else None
         self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
-        self.flat_d = self.opt_d = None
+        self.opt_d = None
         if self.use_gan:
-            # alpha3d never receives a gradient in the reference (unused Parameter, models/p2igan.py:145): keep grad None
-            self.flat_d = FlatGrads((p for n, p in discriminator.named_parameters() if n != "alpha3d"), peer=self.peer_exchange,
-                                    group=process_group)
             self.opt_d = FusedAdam(self.flat_d.params, lr=oc["lr"], betas=betas)
             from . import disc_bwd
             disc_bwd.prepare(discriminator)
