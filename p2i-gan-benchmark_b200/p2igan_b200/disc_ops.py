@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import struct
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 

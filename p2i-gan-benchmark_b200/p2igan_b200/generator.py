@@ -12,8 +12,6 @@ runs the whole trunk in NHWC bf16 through libp2i_sm100a.so:
 """
 from __future__ import annotations
 
-import os
-
 from typing import Dict, List, Optional
 
 import torch

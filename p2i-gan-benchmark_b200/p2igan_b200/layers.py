@@ -9,7 +9,7 @@ activations in NHWC bf16 and calls the ``*_cl`` methods directly.
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn

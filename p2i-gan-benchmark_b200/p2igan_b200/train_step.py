@@ -15,7 +15,7 @@ events; N ranks x b events  ==  one rank x N*b events up to fp32 summation order
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterable, List, Optional
+from typing import Any, Dict, Iterable, List
 
 import torch
 import torch.distributed as dist
