@@ -49,3 +49,11 @@ class P2IDiscriminator(BaseNetwork):
     def forward(self, x):
         from . import disc_ops
         return disc_ops.discriminator_forward(self, x)
+
+    def __getstate__(self):
+        """copy.deepcopy / pickling of the module (EMA copies, torch.save(model)): drop the per-device kernel state (operand
+        sets, device tables, CUDA streams); it is rebuilt on the next forward."""
+        d = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        d = dict(d)
+        d.pop("_p2i_state", None)
+        return d

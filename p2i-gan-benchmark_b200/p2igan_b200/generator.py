@@ -146,6 +146,15 @@ class P2IGenerator(BaseNetwork):
             self._gtable = gt
         return gt
 
+    def __getstate__(self):
+        """copy.deepcopy / pickling of the module: drop transient kernel state (operand caches, gradient arena, CUDA stream)."""
+        d = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        d = dict(d)
+        for k in ("_wcache", "_gtable", "_side"):
+            d.pop(k, None)
+        d["_wcache"] = None
+        return d
+
     def _side_stream(self, device) -> torch.cuda.Stream:
         st = getattr(self, "_side", None)
         if st is None or st.device != torch.device(device):

@@ -369,3 +369,22 @@ def test_experimental_wgrad_variants_match_first_generation(Cin, Cout, H, W, k):
         LIB.call("p2i_set_wgrad_impl", 0)
     torch.cuda.synchronize()
     assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-4
+
+
+def test_deepcopy_after_use_keeps_working():
+    """After a training step the modules hold CUDA streams, device tables and caches: copy.deepcopy must still work (they
+    are dropped from the pickled state and rebuilt), and the copy computes what the original computes."""
+    import copy
+    from p2igan_b200 import build_discriminator, build_generator
+    from p2igan_b200.train_step import GANTrainStep
+    cfg = synth.make_cfg(32, 32)
+    torch.manual_seed(2024)
+    G, D = build_generator(cfg).to(DEV).train(), build_discriminator(cfg).to(DEV).train()
+    ts = GANTrainStep(cfg, G, D)
+    fr, mf, mk = (t.to(DEV) for t in synth.make_batch(2, 16, 32, 32, 12, 3))
+    ts.step(fr, mf, mk)
+    G2, D2 = copy.deepcopy(G).eval(), copy.deepcopy(D).eval()
+    G.eval(); D.eval()
+    with torch.no_grad():
+        assert torch.equal(G(mf, mk), G2(mf, mk))
+        assert torch.equal(D(fr), D2(fr))

@@ -73,3 +73,24 @@ def test_bad_config_errors():
         build_generator(cfg)
     with pytest.raises(KeyError):
         build_generator({"model": {"name": "p2igan"}, "data": {}})
+
+
+def test_modules_deepcopy_and_pickle_roundtrip():
+    """EMA-style copies and torch.save(model) must work: transient kernel state (streams, device tables) is not part of the
+    pickled module, parameters and buffers are."""
+    import copy
+    import io
+    import synth
+    from p2igan_b200 import build_discriminator, build_generator
+    cfg = synth.make_cfg(32, 32)
+    torch.manual_seed(1)
+    for m in (build_generator(cfg), build_discriminator(cfg)):
+        c = copy.deepcopy(m)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        r = torch.load(buf, weights_only=False)
+        for other in (c, r):
+            a, b = m.state_dict(), other.state_dict()
+            assert list(a) == list(b)
+            assert all(torch.equal(a[k], b[k]) for k in a)
