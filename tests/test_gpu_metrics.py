@@ -88,3 +88,25 @@ def test_ssim_matches_oracle_restatement_and_small_images():
     small = RainfallMetricSuite(MetricConfig()).to(DEV)
     small.update(torch.rand(1, 2, 1, 8, 8).to(DEV), torch.rand(1, 2, 1, 8, 8).to(DEV))
     assert math.isnan(small.compute()["ssim"])
+
+
+def test_categorical_scores_cross_check_against_exp1_golden():
+    """Row N4 cross-check: POD / FAR / CSI of the CUDA metric suite vs the values the reference's OTHER implementation
+    (experiments/exp1.categorical_metrics via run_exp1, all pixels, no /3) produced on the same arrays.  HSS is excluded: the
+    two reference files define it with different denominators (metric.py:126-127 vs exp1.py:169-172)."""
+    import os
+    from p2igan_b200.metrics import MetricConfig, RainfallMetricSuite
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = torch.load(os.path.join(root, "tests", "golden", "reference_exp1.pt"), weights_only=False)
+    crop = g["crop"]
+    T, H, W = g["pred"].shape
+    top, left = (H - crop) // 2, (W - crop) // 2
+    pred = g["pred"][:, top:top + crop, left:left + crop].contiguous()
+    truth = g["truth"][:, top:top + crop, left:left + crop].contiguous()
+    suite = RainfallMetricSuite(MetricConfig()).to(DEV)
+    suite.update(pred[None, :, None].to(DEV), truth[None, :, None].to(DEV))
+    m = suite.compute()
+    ref = g["results"]["all_0"]
+    for thr, key in ((0.5, "CAT_0.5"), (2.0, "CAT_2"), (4.0, "CAT_4"), (8.0, "CAT_8")):
+        for ours_k, ref_k in (("pod", "POD"), ("far", "FAR"), ("csi", "CSI")):
+            assert abs(m[f"cat_thr{thr:.2f}/{ours_k}"] - ref[key][ref_k]) < 1e-5, (thr, ours_k)
