@@ -144,9 +144,10 @@ __global__ void gate_points_fwd_kernel(const float* __restrict__ masked, const i
     }
 }
 
-// Backward of the two gates for the single output channel t that feeds `vals`.  Per-point contributions are reduced
-// with warp shuffles first (points are sorted by frame, so a warp almost always shares t), then one shared-memory and
-// one global atomic per weight per block.
+// Backward of the two gates for the single output channel t that feeds `vals`.  Each thread differentiates one point;
+// the sums over points are two small matrix products per block (dw0[j][k] = sum_p dg0[p][j] x[p][k] and, per frame row t,
+// dw1[t][k] = sum_{p: t_p = t} dg1[p] h[p][k]) evaluated from shared memory -- thread (j, k-pair) owns two entries of
+// each -- instead of 272 warp-shuffle reductions per warp; one global atomic per (block, weight) at the end.
 __global__ void __launch_bounds__(128) gate_points_bwd_kernel(const float* __restrict__ masked, const int* __restrict__ pts,
                                                               const int* __restrict__ counts, int cap, const float* __restrict__ w0,
                                                               const float* __restrict__ b0, const float* __restrict__ w1,
@@ -154,92 +155,82 @@ __global__ void __launch_bounds__(128) gate_points_bwd_kernel(const float* __res
                                                               float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
                                                               float* __restrict__ db1, int HW) {
     __shared__ float sw0[256], sw1[256], sb0[16], sb1[16];
-    __shared__ float aw0[256], aw1[256], ab0[16], ab1[16];
+    __shared__ float sX[128][17], sG[128][17], sH[128][17], sG1[128];
+    __shared__ int sT[128];
     const int b = blockIdx.y;
     const int n = counts[b];
     if (static_cast<int>(blockIdx.x * blockDim.x) >= n) return;   // no observed point in this block
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; aw0[i] = 0.f; aw1[i] = 0.f; }
-    if (threadIdx.x < 16) {
-        sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x];
-        ab0[threadIdx.x] = 0.f; ab1[threadIdx.x] = 0.f;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sw0[i] = w0[i]; sw1[i] = w1[i]; }
+    if (threadIdx.x < 16) { sb0[threadIdx.x] = b0[threadIdx.x]; sb1[threadIdx.x] = b1[threadIdx.x]; }
+    const int tid = threadIdx.x;
+    const int oj = tid >> 3, ok = (tid & 7) * 2;          // this thread's output entries (oj, ok) and (oj, ok + 1)
+    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f, ab0 = 0.f, ab1 = 0.f;
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {     // block-uniform trip count
-    const int i = base + threadIdx.x;
-    const bool active = i < n;
-    float x[16], h[16], dg0[16];
-    float dg1 = 0.f;
-    int t = 0;
+        __syncthreads();
+        const int i = base + tid;
+        float x[16], h[16], dg0[16];
+        float dg1 = 0.f;
+        int t = -1;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { x[k] = 0.f; h[k] = 0.f; dg0[k] = 0.f; }
-    if (active) {
-        const int p = pts[static_cast<size_t>(b) * cap + i];
-        t = p / HW;
-        const int pix = p - t * HW;
-        const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
+        for (int k = 0; k < 16; ++k) { x[k] = 0.f; h[k] = 0.f; dg0[k] = 0.f; }
+        if (i < n) {
+            const int p = pts[static_cast<size_t>(b) * cap + i];
+            t = p / HW;
+            const int pix = p - t * HW;
+            const float* xin = masked + static_cast<size_t>(b) * 16 * HW + pix;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = xin[static_cast<size_t>(k) * HW];
+            for (int k = 0; k < 16; ++k) x[k] = xin[static_cast<size_t>(k) * HW];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float g = sb0[j];
+            for (int j = 0; j < 16; ++j) {
+                float g = sb0[j];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) g = fmaf(sw0[j * 16 + k], x[k], g);
-            h[j] = fmaxf(fmaf(x[j], g, x[j]), 0.f);
+                for (int k = 0; k < 16; ++k) g = fmaf(sw0[j * 16 + k], x[k], g);
+                h[j] = fmaxf(fmaf(x[j], g, x[j]), 0.f);
+            }
+            float g1 = sb1[t];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g1 = fmaf(sw1[t * 16 + k], h[k], g1);
+            float ht = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) ht = (k == t) ? h[k] : ht;
+            float dv = dvals[static_cast<size_t>(b) * cap + i];
+            if (fmaf(ht, g1, ht) <= 0.f) dv = 0.f;
+            // v = ht*(1+g1): d g1 = dv*ht ; d h[k] = dg1*w1[t,k] (+ dv*(1+g1) for k == t) ; h[j] = relu(x[j]*(1+g0[j]))
+            dg1 = dv * ht;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float dh = dg1 * sw1[t * 16 + k] + ((k == t) ? dv * (1.f + g1) : 0.f);
+                dg0[k] = (h[k] > 0.f) ? dh * x[k] : 0.f;
+            }
         }
-        float g1 = sb1[t];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) g1 = fmaf(sw1[t * 16 + k], h[k], g1);
-        float ht = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) ht = (k == t) ? h[k] : ht;
-        float dv = dvals[static_cast<size_t>(b) * cap + i];
-        if (fmaf(ht, g1, ht) <= 0.f) dv = 0.f;
-        // v = ht*(1+g1): d g1 = dv*ht ; d h[k] = dg1*w1[t,k] (+ dv*(1+g1) for k == t) ; h[j] = relu(x[j]*(1+g0[j]))
-        dg1 = dv * ht;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float dh = dg1 * sw1[t * 16 + k] + ((k == t) ? dv * (1.f + g1) : 0.f);
-            dg0[k] = (h[k] > 0.f) ? dh * x[k] : 0.f;
+        for (int k = 0; k < 16; ++k) { sX[tid][k] = x[k]; sG[tid][k] = dg0[k]; sH[tid][k] = h[k]; }
+        sG1[tid] = dg1;
+        sT[tid] = t;
+        __syncthreads();
+        // dw0[oj][ok..ok+1] += sum_p dg0[p][oj] * x[p][ok..];   dw1[oj][ok..ok+1] += sum_{p: t_p == oj} dg1[p] * h[p][ok..]
+        for (int p = 0; p < 128; ++p) {
+            const float g = sG[p][oj];
+            a0 = fmaf(g, sX[p][ok], a0);
+            a1 = fmaf(g, sX[p][ok + 1], a1);
+            const float g1p = (sT[p] == oj) ? sG1[p] : 0.f;
+            c0 = fmaf(g1p, sH[p][ok], c0);
+            c1 = fmaf(g1p, sH[p][ok + 1], c1);
         }
-    }
-    // layer 2 (row t of w1): warp-uniform t -> shuffle reduction, else per-lane atomics
-    const unsigned act = __ballot_sync(0xffffffffu, active);
-    const int t0 = __shfl_sync(0xffffffffu, t, act ? (__ffs(act) - 1) : 0);
-    if (__all_sync(0xffffffffu, !active || t == t0)) {
-        const float s = warp_sum(dg1);
-        if (lane == 0 && s != 0.f) atomicAdd(&ab1[t0], s);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float r = warp_sum(dg1 * h[k]);
-            if (lane == 0 && r != 0.f) atomicAdd(&aw1[t0 * 16 + k], r);
-        }
-    } else if (active && dg1 != 0.f) {
-        atomicAdd(&ab1[t], dg1);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) atomicAdd(&aw1[t * 16 + k], dg1 * h[k]);
-    }
-    // layer 1: dw0[j][k] = sum dg0[j]*x[k], db0[j] = sum dg0[j]
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float s = warp_sum(dg0[j]);
-        if (__all_sync(0xffffffffu, dg0[j] == 0.f)) continue;
-        if (lane == 0) atomicAdd(&ab0[j], s);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float r = warp_sum(dg0[j] * x[k]);
-            if (lane == 0 && r != 0.f) atomicAdd(&aw0[j * 16 + k], r);
+        if (tid < 16) {                                    // biases: db0[j] = sum_p dg0[p][j], db1[t] = sum_{p: t_p == t} dg1[p]
+            for (int p = 0; p < 128; ++p) {
+                ab0 += sG[p][tid];
+                ab1 += (sT[p] == tid) ? sG1[p] : 0.f;
+            }
         }
     }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-        if (aw0[k] != 0.f) atomicAdd(&dw0[k], aw0[k]);
-        if (aw1[k] != 0.f) atomicAdd(&dw1[k], aw1[k]);
-    }
-    if (threadIdx.x < 16) {
-        if (ab0[threadIdx.x] != 0.f) atomicAdd(&db0[threadIdx.x], ab0[threadIdx.x]);
-        if (ab1[threadIdx.x] != 0.f) atomicAdd(&db1[threadIdx.x], ab1[threadIdx.x]);
+    if (a0 != 0.f) atomicAdd(&dw0[oj * 16 + ok], a0);
+    if (a1 != 0.f) atomicAdd(&dw0[oj * 16 + ok + 1], a1);
+    if (c0 != 0.f) atomicAdd(&dw1[oj * 16 + ok], c0);
+    if (c1 != 0.f) atomicAdd(&dw1[oj * 16 + ok + 1], c1);
+    if (tid < 16) {
+        if (ab0 != 0.f) atomicAdd(&db0[tid], ab0);
+        if (ab1 != 0.f) atomicAdd(&db1[tid], ab1);
     }
 }
 
