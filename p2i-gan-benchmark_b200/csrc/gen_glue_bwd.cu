@@ -324,6 +324,82 @@ __global__ void __launch_bounds__(256) pyramid_bwd_kernel(const __nv_bfloat16* _
 //   dx [B,16,H,W] f32 : transposed grouped conv + the repeat_interleave(4) path
 //   dw [64,4,9]   f32 : sum_pix dy[pix][oc] * x[g*4+icl][pix + tap]   (register-tiled, atomics at the end)
 // ------------------------------------------------------------------------------------------------
+// thread = (4 consecutive pixels of a row, group g): every LDS.128 of weights (4 input channels of one (tap, oc)) feeds
+// 16 FMAs (4 pixels x 4 ci) -- with one pixel per thread the kernel was shared-memory (MIO) throttled at 4 FMAs per LDS.
+// The 6 gradient pixels a 3-tap row window needs are loaded once per (ky, oc half) as 16-byte vectors; the four group
+// lanes of a pixel quad read the 4 x 32 bytes of each 128-byte pixel row.  Weights: [g][tap][oc][ci], group pitch 580
+// floats (disjoint banks for the four groups of a warp).  Requires W % 4 == 0 (else the one-pixel variant below).
+__global__ void __launch_bounds__(128) stem_bwd_dx4_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w,
+                                                           float* __restrict__ dx, int H, int W) {
+    __shared__ __align__(16) float sw[4 * 580];
+    for (int i = threadIdx.x; i < 4 * 576; i += blockDim.x) {
+        const int ci = i & 3, oc = (i >> 2) & 15, r = i >> 6, tap = r % 9, g = r / 9;
+        sw[g * 580 + (tap * 16 + oc) * 4 + ci] = w[((g * 16 + oc) * 4 + ci) * 9 + tap];
+    }
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int g = threadIdx.x & 3;
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x >> 2)) * 4;
+    if (x0 >= W) return;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const float4* wg = reinterpret_cast<const float4*>(sw + g * 580);
+    for (int yy = blockIdx.y * 4; yy < H && yy < blockIdx.y * 4 + 4; ++yy) {
+        float acc[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int oy = yy - ky + 1;
+            if (oy < 0 || oy >= H) continue;
+            const __nv_bfloat16* rowp = dy + ((static_cast<size_t>(b) * H + oy) * W) * 64 + g * 16;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                // gradient pixels x0-1 .. x0+4 (window position q = 0..5), output channels 8*half .. 8*half+7 of the group
+                float d[6][8];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int ox = x0 - 1 + q;
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                    if (ox >= 0 && ox < W) u = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<size_t>(ox) * 64 + half * 8));
+                    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = unpack_bf16x2(uu[k]);
+                        d[q][2 * k] = f.x; d[q][2 * k + 1] = f.y;
+                    }
+                }
+                // dx[x0+p] += sum_kx dy[x0+p - kx + 1] * w[kx]  ->  window position q = p + 2 - kx
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float4 w4 = wg[(ky * 3 + kx) * 16 + half * 8 + o];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float v = d[p + 2 - kx][o];
+                            acc[p][0] = fmaf(v, w4.x, acc[p][0]);
+                            acc[p][1] = fmaf(v, w4.y, acc[p][1]);
+                            acc[p][2] = fmaf(v, w4.z, acc[p][2]);
+                            acc[p][3] = fmaf(v, w4.w, acc[p][3]);
+                        }
+                    }
+                if (ky == 1) {          // repeat_interleave: output channel oc of the group feeds input channel oc / 4 (centre tap)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) acc[p][(half * 8 + o) >> 2] += d[p + 1][o];
+                }
+            }
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+            *reinterpret_cast<float4*>(dx + (static_cast<size_t>(b) * 16 + g * 4 + ci) * HW + static_cast<size_t>(yy) * W + x0) =
+                make_float4(acc[0][ci], acc[1][ci], acc[2][ci], acc[3][ci]);
+    }
+}
+
 // lane = (pixel, group): the four lanes of a pixel read its 128 contiguous gradient bytes, so a warp request covers
 // 8 pixels x 128 B = 8 cache lines (one pixel per lane with a fixed group touched 32).  Weights: [g][tap][oc][ci] with a
 // group pitch of 580 floats so that the four groups of a warp read disjoint banks (LDS.128 broadcast per group).
@@ -392,10 +468,22 @@ __global__ void __launch_bounds__(256) stem_bwd_dw2_kernel(const __nv_bfloat16* 
         const int tx = tile % ntx, r1 = tile / ntx, y = r1 % H, b = r1 / H;
         const int x0 = tx << 6;
         __syncthreads();
-        for (int e = threadIdx.x; e < 16 * 3 * 66; e += 256) {
-            const int c = e % 66, r2 = e / 66, r = r2 % 3, ch = r2 / 3;
-            const int yi = y + r - 1, xi = x0 + c - 1;
-            sx[ch][r][c] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(x + (static_cast<size_t>(b) * 16 + ch) * HW + static_cast<size_t>(yi) * W + xi) : 0.f;
+        {   // 48 patch rows (16 channels x 3 image rows) of 66 floats: one warp per row, no per-element div/mod
+            const int lane = threadIdx.x & 31;
+            for (int row = threadIdx.x >> 5; row < 48; row += 8) {
+                const int ch = row / 3, r = row - ch * 3;
+                const int yi = y + r - 1;
+                const bool rowok = yi >= 0 && yi < H;
+                const float* src = x + (static_cast<size_t>(b) * 16 + ch) * HW + static_cast<size_t>(rowok ? yi : 0) * W + x0 - 1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < 66) {
+                        const int xi = x0 + c - 1;
+                        sx[ch][r][c] = (rowok && xi >= 0 && xi < W) ? __ldg(src + c) : 0.f;
+                    }
+                }
+            }
         }
         for (int e = threadIdx.x; e < 64 * 8; e += 256) {
             const int px = e >> 3, q = e & 7;
@@ -477,7 +565,11 @@ extern "C" int p2i_pyramid_bwd(const void* stem, const void* dx4, const void* dx
 extern "C" int p2i_stem_bwd(const void* dy, const float* x, const float* w, float* dx, float* dw, int B, int H, int W,
                             void* stream) {
     P2I_CHECK_ARG(dy && x && w && (dx || dw), "stem_bwd: null pointer");
-    if (dx) {        // dx == NULL / dw == NULL: only the other gradient (the two kernels are independent; callers may run them on two streams)
+    if (dx && W % 4 == 0) {       // dx == NULL / dw == NULL: only the other gradient (two independent kernels)
+        dim3 grid(cdiv(W, 128), cdiv(H, 4), B);
+        stem_bwd_dx4_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
+        P2I_CHECK_LAUNCH("stem_bwd_dx4_kernel");
+    } else if (dx) {
         dim3 grid(cdiv(W, 32), cdiv(H, 4), B);
         stem_bwd_dx_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dy), w, dx, H, W);
         P2I_CHECK_LAUNCH("stem_bwd_dx_kernel");

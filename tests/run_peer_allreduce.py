@@ -87,6 +87,7 @@ def train_losses(peer):
     from p2igan_b200 import build_discriminator, build_generator
     from p2igan_b200.train_step import GANTrainStep
     cfg = synth.make_cfg(32, 32)
+    cfg["train"]["optimizer"]["lr"] = 1e-6          # two runs are compared: keep them on one trajectory (test_gpu_trainer.py _LR_NOTE)
     torch.manual_seed(2024)
     G, D = build_generator(cfg).to(dev).train(), build_discriminator(cfg).to(dev).train()
     ts = GANTrainStep(cfg, G, D, peer_exchange=peer)
@@ -102,9 +103,9 @@ ln, pn = train_losses(False)
 lp, pp = train_losses(True)
 for a, b in zip(ln, lp):
     for k in a:
-        assert abs(a[k] - b[k]) < 1e-2 * abs(a[k]) + 1e-5, (k, a[k], b[k])
+        assert abs(a[k] - b[k]) < 2e-3 * abs(a[k]) + 1e-5, (k, a[k], b[k])
 d = (pn - pp).abs()
-assert float(d.max()) <= 3e-3 and float(d.mean()) < 2e-5, (float(d.max()), float(d.mean()))
+assert float(d.max()) <= 3e-5 and float(d.mean()) < 2e-7, (float(d.max()), float(d.mean()))
 # data-parallel invariant: parameters stay identical across ranks
 ref = pp.clone()
 dist.broadcast(ref, 0)

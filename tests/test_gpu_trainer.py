@@ -44,6 +44,10 @@ def test_batch_prep_u8_matches_reference_golden():
         assert torch.equal(ours[0].cpu(), ref.permute(0, 3, 1, 2))
 
 
+# _LR_NOTE: Adam with beta1 = 0 takes lr-sized sign-like steps, so elements whose gradient sits at the noise floor of the fp32
+# atomics' summation order can move in opposite directions in two otherwise identical runs; at the reference's lr = 1e-4 that
+# seeds a chaotic ~1-3 % drift of the losses within a few steps.  The tests that compare two RUNS of the loop (resume, graph
+# replay) use lr = 1e-6: the mechanics are identical, the drift is 100x smaller and the comparisons can be tight.
 def _batches(n, seed0):
     return [tuple(t.to(DEV) for t in synth.make_batch(2, 16, 32, 32, 12, seed0 + i)) for i in range(n)]
 
@@ -54,6 +58,7 @@ def test_checkpoint_format_and_resume(tmp_path):
     from p2igan_b200 import Trainer
     cfg = synth.make_cfg(32, 32)
     cfg["train"]["log_step"] = 1
+    cfg["train"]["optimizer"]["lr"] = 1e-6        # keeps the two runs on the same trajectory (see _LR_NOTE)
     data = _batches(3, 300)
     a = Trainer(cfg, use_graphs=False)
     a.train_epoch(data)
@@ -73,9 +78,9 @@ def test_checkpoint_format_and_resume(tmp_path):
     tot = num = 0.0
     for k, v in a.generator.state_dict().items():
         d = (v - c.generator.state_dict()[k]).abs()
-        assert float(d.max()) <= 3e-3, k
+        assert float(d.max()) <= 3e-5, k
         tot += float(d.sum()); num += d.numel()
-    assert tot / num < 2e-5
+    assert tot / num < 2e-7
     # Adam step counters continue across the resume
     assert float(next(iter(c.opt_g.state.values()))["step"]) == 3.0
 
@@ -86,6 +91,7 @@ def test_graphed_trainer_and_validation_loss():
     from p2igan_b200 import Trainer
     cfg = synth.make_cfg(32, 32)
     cfg["train"]["log_step"] = 1
+    cfg["train"]["optimizer"]["lr"] = 1e-6        # see _LR_NOTE
     data = _batches(4, 400)
     logs_e, logs_g = [], []
     e = Trainer(cfg, use_graphs=False, log_fn=lambda s, r: logs_e.append(r))
@@ -95,9 +101,9 @@ def test_graphed_trainer_and_validation_loss():
     assert len(logs_e) == len(logs_g) == 4
     for it, (a, b) in enumerate(zip(logs_e, logs_g)):
         for k in ("rec", "dis", "total"):
-            # both loops take the same steps; they drift apart only through lr-sized sign flips of noise-floor elements
-            # (Adam, beta1 = 0) seeded by the atomics' summation order -- the temporal-KL term amplifies that to ~1 %
-            assert abs(a[k] - b[k]) < 3e-2 * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
+            assert abs(a[k] - b[k]) < 2e-3 * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
+    moved = sum(float((v - w_).abs().sum()) for v, w_ in zip(g.generator.state_dict().values(), Trainer(cfg, use_graphs=False).generator.state_dict().values()))
+    assert moved > 0.0                               # the replayed steps really updated the parameters
     val = _batches(2, 900)
     got = g.evaluate_rec_loss(val)
     sd = {k: v.detach().cpu() for k, v in g.generator.state_dict().items()}

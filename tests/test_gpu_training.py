@@ -253,6 +253,7 @@ def test_three_graph_dp_step_equals_eager_step():
     from p2igan_b200 import build_discriminator, build_generator
     from p2igan_b200.train_step import GANTrainStep, GraphedDPStep
     cfg = synth.make_cfg(32, 32)
+    cfg["train"]["optimizer"]["lr"] = 1e-6     # two RUNS are compared: keep them on one trajectory (tests/test_gpu_trainer.py _LR_NOTE)
     batches = [tuple(t.to(DEV) for t in synth.make_batch(2, 16, 32, 32, 12, 200 + i)) for i in range(3)]
 
     def run(graphed):
@@ -282,7 +283,7 @@ def test_three_graph_dp_step_equals_eager_step():
     for it, (a, b) in enumerate(zip(le, lg)):
         # iteration 0 starts from identical parameters: only the atomics' summation order differs.  Later iterations
         # inherit lr-sized sign flips of noise-floor elements (Adam, beta1 = 0), hence the looser bound.
-        tol = 2e-4 if it == 0 else 1e-2
+        tol = 2e-4 if it == 0 else 2e-3
         for k in a:
             assert abs(a[k] - b[k]) < tol * abs(a[k]) + 1e-5, (it, k, a[k], b[k])
     # parameters: identical up to sign flips of noise-floor elements (each worth up to ~2 lr per step, more when the
@@ -290,9 +291,9 @@ def test_three_graph_dp_step_equals_eager_step():
     tot = num = 0.0
     for k in ge:
         d = (ge[k] - gg[k]).abs()
-        assert float(d.max()) <= 3e-3, (k, float(d.max()))
+        assert float(d.max()) <= 3e-5, (k, float(d.max()))
         tot += float(d.sum()); num += d.numel()
-    assert tot / num < 2e-5, tot / num
+    assert tot / num < 2e-7, tot / num
 
 
 def test_peer_allreduce_two_gpus():
