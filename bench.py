@@ -244,17 +244,19 @@ class ConvTimer:
 
     @staticmethod
     def event_pair_overhead_ms(n: int = 200) -> float:
-        """Elapsed time CUDA reports between two events recorded back to back around a trivial kernel, minus nothing:
-        the per-pair floor (launch + timestamp granularity) that every bracketed launch carries.  Measured on the idle
-        stream with an empty-ish kernel (a 1-element fill) so that it can be subtracted from the bracketed conv launches."""
+        """What CUDA reports for an event pair around an EMPTY piece of work (a 1-element in-place add): the floor every
+        bracketed launch carries (two timestamps + one kernel dispatch).  Measured like the launches themselves -- enqueued
+        behind a device-side sleep, so that it is GPU-side cost and not the host's pace of issuing."""
         x = torch.zeros(1, device="cuda")
         pairs = []
+        torch.cuda.synchronize()
+        torch.cuda._sleep(100_000_000)
         for _ in range(n):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
+            x.add_(1)
             e.record()
             pairs.append((s, e))
-            x.add_(1)
         torch.cuda.synchronize()
         v = sorted(s.elapsed_time(e) for s, e in pairs)
         return v[len(v) // 2]
@@ -424,20 +426,25 @@ def run_ours(args):
     # second pass with the overlap on (as in the timed step) are reported next to them.
     from p2igan_b200 import set_stream_overlap
     psteps = min(args.steps, 4)
+
+    def timed_pass():
+        """Eager steps with events around every conv launch.  Each step is enqueued behind a ~100 ms device-side sleep so
+        that the whole step sits in the launch queue before the GPU starts it: the events then bracket kernel time, not the
+        host's launch latency (an eager step is issued in ~7 ms, about as long as it runs)."""
+        t_ = ConvTimer()
+        t_.install()
+        for i in range(psteps):
+            torch.cuda.synchronize()
+            torch.cuda._sleep(200_000_000)
+            eager(*batches[i % 4])
+        r_ = t_.result()
+        t_.remove()
+        return r_
+
     set_stream_overlap(False)
-    timer = ConvTimer()
-    timer.install()
-    for i in range(psteps):
-        eager(*batches[i % 4])
-    kt = timer.result()
-    timer.remove()
+    kt = timed_pass()
     set_stream_overlap(True)
-    timer2 = ConvTimer()
-    timer2.install()
-    for i in range(psteps):
-        eager(*batches[i % 4])
-    kt_ov = timer2.result()
-    timer2.remove()
+    kt_ov = timed_pass()
     ev_ms = ConvTimer.event_pair_overhead_ms()
 
     if train and ts.peer_exchange:
@@ -453,9 +460,8 @@ def run_ours(args):
         metric, wl = WORKLOADS[args.workload]
         ig_ms, ig_n, ig_fl = kt["igemm"]
         wg_ms, wg_n, wg_fl = kt["wgrad"]
-        # an event pair recorded back to back already reads ev_ms apart: that floor is not kernel time
-        ig_ms = max(ig_ms - ig_n * ev_ms, 1e-6) if ig_n else ig_ms
-        wg_ms = max(wg_ms - wg_n * ev_ms, 1e-6) if wg_n else wg_ms
+        # no correction is applied: each bracket also contains the two timestamps and the kernel dispatch (ev_ms measures an
+        # event pair around an empty kernel, reported for information), so `achieved` is a lower bound of the kernel's rate
         ig_tf = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else None
         wg_tf = wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None
         if train:
@@ -484,9 +490,10 @@ def run_ours(args):
                                                              "profiles/r1_conv_halo_ncu.txt (ncu --set full, train step, B=16)",
                          "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                          "kernel_ms_per_step": ig_ms / psteps, "launches_per_step": ig_n // psteps,
-                         "event_pair_floor_us_subtracted_per_launch": ev_ms * 1e3,
-                         "measured": "side-stream overlap off (kernel alone); with the overlap on, as in the timed step: "
-                                     f"{max(kt_ov['igemm'][0] - kt_ov['igemm'][1] * ev_ms, 1e-6) / psteps:.3f} ms/step for the same launches",
+                         "event_pair_around_empty_kernel_us": ev_ms * 1e3,
+                         "measured": "CUDA events around every launch, each eager step enqueued behind a device-side sleep (no host "
+                                     "pacing in the brackets), side-stream overlap off (kernel alone), no overhead subtracted; with the "
+                                     f"overlap on, as in the timed step: {kt_ov['igemm'][0] / psteps:.3f} ms/step for the same launches",
                          "algorithmic_gflop_per_step": ig_fl / psteps / 1e9,
                          "wgrad_kernel": {"achieved": wg_tf, "frac": (wg_tf / sustained) if wg_tf else None,
                                           "kernel_ms_per_step": wg_ms / psteps, "launches_per_step": wg_n // psteps,
