@@ -298,13 +298,19 @@ def test_three_graph_dp_step_equals_eager_step():
 
 def test_peer_allreduce_two_gpus():
     """NVLink peer-memory all-reduce vs NCCL, graph replay, and a DP training step (tests/run_peer_allreduce.py under torchrun)."""
+    import os
     import subprocess
     import sys as _sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs on one node")
+    import socket
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sk = socket.socket()
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
+    sk.close()
     r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_peer_allreduce.py")],
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "run_peer_allreduce.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PEER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
