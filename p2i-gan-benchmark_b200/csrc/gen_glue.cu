@@ -108,13 +108,12 @@ __global__ void __launch_bounds__(256) upmod_fwd_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ bias, const __nv_bfloat16* __restrict__ skip,
                                                         __nv_bfloat16* __restrict__ out, int B, int h, int w, int C) {
     const int cg = C >> 3;
-    const long long total = static_cast<long long>(B) * 4 * h * w * cg;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int total = B * 4 * h * w * cg;                      // < 2^31 (checked on the host): 32-bit index arithmetic
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cg);
-    long long pix = idx / cg;
+    const int pix = idx / cg, c8 = idx - pix * cg;
     const int H2 = 2 * h, W2 = 2 * w;
-    const int X = static_cast<int>(pix % W2), Y = static_cast<int>((pix / W2) % H2), b = static_cast<int>(pix / (static_cast<long long>(W2) * H2));
+    const int r_ = pix / W2, X = pix - r_ * W2, b = r_ / H2, Y = r_ - b * H2;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
     const float fy = sy * Y, fx = sx * X;
@@ -234,6 +233,7 @@ extern "C" int p2i_upmod_fwd(const void* z, const float* pos, const float* bias,
     P2I_CHECK_ARG(z && pos && bias && out, "upmod_fwd: null pointer");
     P2I_CHECK_ARG(C % 8 == 0 && C > 0, "upmod_fwd: C=%d must be a multiple of 8", C);
     const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+    P2I_CHECK_ARG(total < (1ll << 31), "upmod_fwd: tensor too large for 32-bit indexing");
     upmod_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(z), pos, bias, static_cast<const __nv_bfloat16*>(skip),
         static_cast<__nv_bfloat16*>(out), B, h, w, C);

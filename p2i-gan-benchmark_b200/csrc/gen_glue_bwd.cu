@@ -23,9 +23,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     for (int o = 0; o < 4; ++o)
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[o][i] = 0.f;
-    for (long long p = static_cast<long long>(blockIdx.x) * 64 + (threadIdx.x >> 2); p < npix;
-         p += static_cast<long long>(gridDim.x) * 64) {
-        const int b = static_cast<int>(p / HW), pix = static_cast<int>(p - static_cast<long long>(b) * HW);
+    const int np32 = static_cast<int>(npix);                    // < 2^31 (checked on the host)
+    for (int p = blockIdx.x * 64 + (threadIdx.x >> 2); p < np32; p += gridDim.x * 64) {
+        const int b = p / HW, pix = p - b * HW;
         float dz[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
@@ -101,17 +101,15 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
     __syncthreads();
     const int cg = C >> 3;
-    const long long total = static_cast<long long>(B) * 4 * h * w * cg;
+    const int total = B * 4 * h * w * cg;                      // < 2^31 (checked on the host): 32-bit index arithmetic
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
     float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c8 = static_cast<int>(idx % cg);
-        const long long pix = idx / cg;
-        const int X = static_cast<int>(pix % W2), Y = static_cast<int>((pix / W2) % H2);
-        const int b = static_cast<int>(pix / (static_cast<long long>(W2) * H2));
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c8 = idx & (cg - 1);                         // cg is a power of two (checked on the host)
+        const int pix = idx / cg;
+        const int r_ = pix / W2, X = pix - r_ * W2, b = r_ / H2, Y = r_ - b * H2;
         const float fy = sy * Y, fx = sx * X;
         const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
         const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
@@ -154,7 +152,7 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
     }
     // bias gradient: registers -> (lanes sharing a channel group folded by shuffles when cg < 32) -> shared -> global
     {
-        const int c8 = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) % cg);
+        const int c8 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) & (cg - 1));
         for (int off = 16; off >= cg; off >>= 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) dbv[k] += __shfl_xor_sync(0xffffffffu, dbv[k], off);
@@ -175,12 +173,11 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) upmod_bwd_lo_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dz,
                                                            int B, int h, int w, int C) {
     const int cg = C >> 3;
-    const long long total = static_cast<long long>(B) * h * w * cg;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int total = B * h * w * cg;                          // < 2^31 (checked on the host)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cg);
-    const long long pix = idx / cg;
-    const int x = static_cast<int>(pix % w), y = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const int pix = idx / cg, c8 = idx - pix * cg;
+    const int r_ = pix / w, x = pix - r_ * w, b = r_ / h, y = r_ - b * h;
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
@@ -524,6 +521,7 @@ extern "C" int p2i_head_bwd(const float* dout, const float* out, const void* x, 
                             int H, int W, void* stream) {
     P2I_CHECK_ARG(dout && out && x && w && dx && dw, "head_bwd: null pointer");
     const long long npix = static_cast<long long>(B) * H * W;
+    P2I_CHECK_ARG(npix * 64 < (1ll << 31), "head_bwd: tensor too large for 32-bit indexing");
     long long blocks = (npix + 63) / 64;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     head_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
@@ -537,6 +535,7 @@ extern "C" int p2i_upmod_bwd(const void* z, const float* pos, const float* bias,
     P2I_CHECK_ARG(z && pos && bias && dout && g_scratch && dz && dbias && dpos, "upmod_bwd: null pointer");
     P2I_CHECK_ARG(C % 64 == 0 && (C & (C - 1)) == 0, "upmod_bwd: C=%d must be a power of two >= 64", C);
     const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
+    P2I_CHECK_ARG(total < (1ll << 31), "upmod_bwd: tensor too large for 32-bit indexing");
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     upmod_bwd_hi_kernel<<<static_cast<unsigned>(blocks), 256, C * sizeof(float), as_stream(stream)>>>(
