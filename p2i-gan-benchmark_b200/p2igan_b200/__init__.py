@@ -13,7 +13,7 @@ from ._overlap import set_stream_overlap  # noqa: F401
 from .data import prepare_batch, prepare_batch_u8  # noqa: F401
 from .discriminator import P2IDiscriminator  # noqa: F401
 from .generator import P2IGenerator  # noqa: F401
-from .infer import sliding_window_infer  # noqa: F401
+from .infer import run_inference, sliding_window_infer  # noqa: F401
 from .losses import ReconstructionLoss, gan_loss  # noqa: F401
 from .metrics import MetricConfig, RainfallMetricSuite, transform  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
@@ -23,4 +23,4 @@ from .trainer import Trainer  # noqa: F401
 
 __all__ = ["P2IGenerator", "P2IDiscriminator", "build_generator", "build_discriminator", "ReconstructionLoss", "gan_loss",
            "MetricConfig", "RainfallMetricSuite", "transform", "FusedAdam", "GANTrainStep", "GraphedStep", "FlatGrads",
-           "GraphedDPStep", "sliding_window_infer", "Trainer", "prepare_batch", "prepare_batch_u8", "set_stream_overlap"]
+           "GraphedDPStep", "sliding_window_infer", "run_inference", "Trainer", "prepare_batch", "prepare_batch_u8", "set_stream_overlap"]

@@ -37,3 +37,33 @@ def sliding_window_infer(generator, masked_frames: torch.Tensor, masks: torch.Te
     out = torch.empty(L, 1, H, W, dtype=torch.float32, device=preds.device)
     LIB.call("p2i_window_blend", ptr(preds), ptr(out), L, H * W, stride, step, len(starts), float(output_scale), stream())
     return out
+
+
+def run_inference(generator, events, output_path: str, attrs=None, stride: int = 16, overlap: int = 12, output_scale: float = 255.0,
+                  passes: int = 1, overwrite: bool = False, max_windows_per_batch: int = 64):
+    """The event loop of scripts/infer.py:194-260 around ``sliding_window_infer``: every event (``events`` yields
+    (frames, masked_frames, masks), each [1, L, 1, H, W] on the generator's device -- the reference's test loader has batch
+    size 1) becomes dataset ``event_XX`` [L, 1, H, W] float32 of a zarr-v2 group; with ``passes`` > 1 the running mean over
+    passes is kept (infer.py:258-260; the generator is deterministic, so further passes only matter for stochastic masks).
+    One device->host copy per event.  Returns the list of dataset names."""
+    from . import zarr_io
+    group = zarr_io.open_group(str(output_path), dict(attrs or {}, passes=int(passes), output_scale=float(output_scale)),
+                               overwrite=overwrite)
+    names = []
+    was_training = generator.training
+    generator.eval()
+    try:
+        for pass_idx in range(max(1, int(passes))):
+            for offset, (_, masked, masks) in enumerate(events() if callable(events) else events):
+                comp = sliding_window_infer(generator, masked, masks, stride=stride, overlap=overlap, output_scale=output_scale,
+                                            max_windows_per_batch=max_windows_per_batch).cpu().numpy()
+                name = f"event_{offset + 1:02d}"
+                if pass_idx == 0:
+                    names.append(name)
+                else:
+                    cur = zarr_io.read_array(group, name)
+                    comp = cur + (comp - cur) / float(pass_idx + 1)
+                zarr_io.write_array(group, name, comp)
+    finally:
+        generator.train(was_training)
+    return names

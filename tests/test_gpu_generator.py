@@ -4,6 +4,8 @@ Tolerances (stated, bf16 activations with fp32 accumulation vs the fp32 oracle; 
   single conv            rel-L2 <= 5e-3           IDW (non-tie queries)   abs <= 2e-5 vs exact oracle
   whole G, pre-tanh      rel-L2 <= 1.5e-2         G output                max-abs <= 5e-2, mean-abs <= 5e-3
 """
+import os
+
 import pytest
 import torch
 
@@ -233,6 +235,29 @@ def test_sliding_window_inference_matches_oracle(L):
     d = (out.cpu() - ref).abs() / 255.0
     assert float(d.max()) < 5e-2 and float(d.mean()) < 5e-3
     assert float(out.min()) >= 0.0
+
+
+def test_run_inference_writes_reference_layout(tmp_path):
+    """scripts/infer.py's event loop: one zarr-v2 dataset event_XX [L,1,H,W] float32 per event, run attributes in .zattrs,
+    multi-pass running mean (idempotent for a deterministic generator), refusal to clobber an existing output."""
+    import json
+    import numpy as np
+    from p2igan_b200 import run_inference, zarr_io
+    G, sd = _generator_pair(32, 32, 2024, True)
+    events = [tuple(t.to(DEV) for t in synth.make_batch(1, L, 32, 32, 12, 40 + i)) for i, L in enumerate((16, 21))]
+    out = str(tmp_path / "testp2igan.zarr")
+    names = run_inference(G, events, out, attrs={"model_name": "p2igan", "checkpoint": "none"}, passes=2)
+    assert names == ["event_01", "event_02"] and list(zarr_io.list_arrays(out)) == names
+    att = json.load(open(os.path.join(out, ".zattrs")))
+    assert att["passes"] == 2 and att["output_scale"] == 255.0 and att["model_name"] == "p2igan"
+    for name, (fr, mf, mk) in zip(names, events):
+        got = zarr_io.read_array(out, name)
+        ref = O.sliding_window_infer(sd, mf.cpu(), mk.cpu()).numpy()
+        assert got.shape == ref.shape and got.dtype == np.float32
+        d = np.abs(got - ref) / 255.0
+        assert float(d.max()) < 5e-2 and float(d.mean()) < 5e-3 and float(got.min()) >= 0.0
+    with pytest.raises(FileExistsError):
+        run_inference(G, events, out)
 
 
 def test_drop_in_import_paths():
