@@ -1,4 +1,6 @@
 // Convolution as a tcgen05 implicit GEMM for sm_100a: spatial stride 1, taps k in {1,2,3} (x KT in {1,3} frames).
+// FIRST GENERATION: since conv_igemm_halo.cu exists this kernel only takes the shapes that one declines (channel counts
+// that are not multiples of 64, the thin direct-conv path, p2i_set_conv_impl(1) for A/B runs); the dispatch lives in run_igemm.
 //
 //   reference call sites
 //     F.conv2d in DOConv2d._conv_forward (p2igan_bench/modules/deconv_pytorch.py:104-109) with the ReLU /
