@@ -25,8 +25,11 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: NCCL's own messages (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." on some boxes), so the
+# process-level stdout (fd 1) is pointed at stderr for the whole run and the JSON line goes to a private copy of the original.
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -183,7 +186,7 @@ def run_reference(args):
                              "sample": f"{n_events} events/step x {steps} steps of the same workload (oracle/p2i_oracle.py: "
                                        "torch CPU fp32 restatement of the reference, reference-style cdist/topk IDW)"},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -506,7 +509,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
                                     "sample": "4 events/step x 5 timed steps (+1 warm-up) of the same workload (oracle/p2i_oracle.py, torch "
                                               "CPU fp32 restatement of the reference, reference-style IDW)"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
