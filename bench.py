@@ -195,17 +195,37 @@ class ConvTimer:
     with the ALGORITHMIC FLOPs of each launch (space-to-depth k=2 layers count 9/16 of the executed MACs, the
     channel-padded first 2-D discriminator layer 16/64)."""
 
-    def __init__(self):
+    CONV_ENTRY = ("p2i_conv_igemm", "p2i_conv2d_igemm_fwd", "p2i_conv_wgrad", "p2i_conv2d_wgrad")
+
+    def __init__(self, group_runs: bool = False):
+        """group_runs: one event pair per RUN of consecutive launches of the same kind (e.g. the 8 convs of an EBlock plus the
+        following projection) instead of one per launch -- the run ends as soon as any other kernel of this library is
+        launched.  Only valid when everything runs on one stream (side-stream overlap off)."""
+        self.group = group_runs
         self.ev = {"igemm": [], "wgrad": []}
+        self.n = {"igemm": 0, "wgrad": 0}
         self.flops = {"igemm": 0.0, "wgrad": 0.0}
+        self.open = None                       # (kind, start event) of the run being bracketed
+
+    def _close(self):
+        if self.open is not None:
+            kind, s = self.open
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev[kind].append((s, e))
+            self.open = None
 
     def _rec(self, kind, fl, fn, *a, **k):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        if not (self.group and self.open is not None and self.open[0] == kind):
+            self._close()
+            s = torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.open = (kind, s)
         r = fn(*a, **k)
-        e.record()
-        self.ev[kind].append((s, e))
+        self.n[kind] += 1
         self.flops[kind] += fl
+        if not self.group:
+            self._close()
         return r
 
     def install(self):
@@ -240,10 +260,23 @@ class ConvTimer:
         ops.conv2d_cl, ops.conv2d_wgrad = cl, wg
         disc_ops.conv_igemm, disc_ops.conv_wgrad = dig, dwg
         disc_bwd.conv_igemm, disc_bwd.conv_wgrad = dig, dwg
+        if self.group:                         # any other kernel of the library ends the open run BEFORE it is launched
+            from p2igan_b200._lib import LIB
+            lib_call = type(LIB).call
+
+            def call(name, *args):
+                if name not in self.CONV_ENTRY:
+                    self._close()
+                return lib_call(LIB, name, *args)
+            LIB.call = call
 
     def remove(self):
         from p2igan_b200 import disc_bwd, disc_ops, ops
+        from p2igan_b200._lib import LIB
+        self._close()
         ops.conv2d_cl, ops.conv2d_wgrad, disc_ops.conv_igemm, disc_ops.conv_wgrad, disc_bwd.conv_igemm, disc_bwd.conv_wgrad = self._orig
+        if "call" in LIB.__dict__:
+            del LIB.call
 
     @staticmethod
     def event_pair_overhead_ms(n: int = 200) -> float:
@@ -265,11 +298,12 @@ class ConvTimer:
         return v[len(v) // 2]
 
     def result(self):
+        self._close()
         torch.cuda.synchronize()
         out = {}
         for k in ("igemm", "wgrad"):
             ms = sum(s.elapsed_time(e) for s, e in self.ev[k])
-            out[k] = (ms, len(self.ev[k]), self.flops[k])
+            out[k] = (ms, self.n[k], self.flops[k], len(self.ev[k]))
         return out
 
 
@@ -430,11 +464,11 @@ def run_ours(args):
     from p2igan_b200 import set_stream_overlap
     psteps = min(args.steps, 4)
 
-    def timed_pass():
-        """Eager steps with events around every conv launch.  Each step is enqueued behind a ~100 ms device-side sleep so
+    def timed_pass(group_runs):
+        """Eager steps with events around the conv launches (per run of consecutive launches or per launch).  Each step is enqueued behind a ~100 ms device-side sleep so
         that the whole step sits in the launch queue before the GPU starts it: the events then bracket kernel time, not the
         host's launch latency (an eager step is issued in ~7 ms, about as long as it runs)."""
-        t_ = ConvTimer()
+        t_ = ConvTimer(group_runs)
         t_.install()
         for i in range(psteps):
             torch.cuda.synchronize()
@@ -445,9 +479,9 @@ def run_ours(args):
         return r_
 
     set_stream_overlap(False)
-    kt = timed_pass()
+    kt = timed_pass(True)
     set_stream_overlap(True)
-    kt_ov = timed_pass()
+    kt_ov = timed_pass(False)
     ev_ms = ConvTimer.event_pair_overhead_ms()
 
     if train and ts.peer_exchange:
@@ -461,8 +495,8 @@ def run_ours(args):
         sustained, burst, hbm, src = peaks()
         events = B * world * args.steps
         metric, wl = WORKLOADS[args.workload]
-        ig_ms, ig_n, ig_fl = kt["igemm"]
-        wg_ms, wg_n, wg_fl = kt["wgrad"]
+        ig_ms, ig_n, ig_fl, ig_br = kt["igemm"]
+        wg_ms, wg_n, wg_fl, wg_br = kt["wgrad"]
         # no correction is applied: each bracket also contains the two timestamps and the kernel dispatch (ev_ms measures an
         # event pair around an empty kernel, reported for information), so `achieved` is a lower bound of the kernel's rate
         ig_tf = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else None
@@ -494,8 +528,10 @@ def run_ours(args):
                          "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                          "kernel_ms_per_step": ig_ms / psteps, "launches_per_step": ig_n // psteps,
                          "event_pair_around_empty_kernel_us": ev_ms * 1e3,
-                         "measured": "CUDA events around every launch, each eager step enqueued behind a device-side sleep (no host "
-                                     "pacing in the brackets), side-stream overlap off (kernel alone), no overhead subtracted; with the "
+                         "event_brackets_per_step": ig_br // psteps,
+                         "measured": "CUDA events around every RUN of consecutive conv launches (a run ends when any other kernel is "
+                                     "launched), each eager step enqueued behind a device-side sleep (no host pacing in the brackets), "
+                                     "side-stream overlap off (kernels alone), no overhead subtracted; per-launch brackets with the "
                                      f"overlap on, as in the timed step: {kt_ov['igemm'][0] / psteps:.3f} ms/step for the same launches",
                          "algorithmic_gflop_per_step": ig_fl / psteps / 1e9,
                          "wgrad_kernel": {"achieved": wg_tf, "frac": (wg_tf / sustained) if wg_tf else None,
