@@ -31,6 +31,12 @@ int p2i_abi_version(void);
 const char* p2i_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's `gpu_launches`). */
 long long p2i_launch_count(void);
+/* Debug: which kernel variant the calling thread's most recent conv entry point launched.
+ *   2000000 + MB*100000 + NT*100 + RES*10 + CG : conv_halo_kernel<NT,RES,CG> (M blocking MB)
+ *   1000000 + NT*100                           : first-generation conv_igemm_kernel<NT>
+ *   3000000 + nt*100 + stacked*10              : conv_wgrad_kernel        4000000 + mode : conv_wgrad2_kernel
+ * The parity tests assert that the shapes they run select the instantiations the benchmark's train step launches. */
+int p2i_conv_last_variant(void);
 
 /* ---------------------------------------------------------------------------------------------
  * InputBlock  (p2igan_bench/modules/layer.py:307-361; gate :296-304; idw_3d_knn :259-293)
@@ -175,6 +181,11 @@ int p2i_stem_fwd(const float* x, const float* w, void* y, int B, int H, int W, v
 /* DownsampleDuplicateChannels x3 fused (layer.py:200-214; p2igan.py:81-83): from the stem output
  * [B,H,W,64] produce x4 [B,H/4,W/4,256] and x8 [B,H/8,W/8,512] (x2 is never consumed, p2igan.py:100). */
 int p2i_pyramid_fwd(const void* stem, void* x4, void* x8, int B, int H, int W, void* stream);
+/* One standalone DownsampleDuplicateChannels level on the reference's NCHW f32 layout (layer.py:205-214): x [B,C,H,W] ->
+ * y [B,2C,H/2,W/2], y[:,2c] = y[:,2c+1] = max_pool2d(x[:,c], 2, 2).  The generator uses the fused pyramid above instead. */
+int p2i_downsample_dup_fwd(const float* x, float* y, int B, int C, int H, int W, void* stream);
+/* dx [B,C,H,W] (overwritten) = gradient routed to the first arg-max of every 2x2 window, summed over the two duplicates. */
+int p2i_downsample_dup_bwd(const float* x, const float* dy, float* dx, int B, int C, int H, int W, void* stream);
 
 /* UPPos after hoisting the 1x1 projection below the upsample (layer.py:384-399):
  * out = relu( 2*sigmoid(pos) * bilinear_x2_align_corners(z) + bias ) [+ skip]
@@ -315,6 +326,13 @@ int p2i_gan_loss_bwd(const float* logits, long long n, int mode, float label, co
  * metric.py:168-169).  apply_transform selects whether MAE/RMSE use the transformed values (metric.py:46-48). */
 int p2i_metrics_update(const float* pred, const float* target, int N, int H, int W, const float* thresholds, int n_thr,
                        const int* scales, int n_scale, int apply_transform, double* scratch, float* state, void* stream);
+
+/* FractionalSkillScoreMetric.update (metric.py:151-169) for ONE (threshold, box size) pair with an arbitrary box size
+ * 1 <= scale <= 32 (the fused pass above covers the default boxes {1,2,4,8}; MetricConfig.scales takes any, :186-191):
+ * avg_pool2d(mask, scale, stride 1, pad scale/2) with the zero padding counted, (H + 2*(scale/2) - scale + 1)^2 outputs.
+ * scratch: double [2] zero-filled once (left clean); state f32 [2] += {1 - mean_num/(mean_den + 1e-10), 1}. */
+int p2i_fss_update(const float* pred, const float* target, int N, int H, int W, float threshold, int scale, double* scratch,
+                   float* state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser  (torch.optim.Adam as used by scripts/train.py:125-136)

@@ -110,24 +110,20 @@ def idw_integer_keys(tz: Tensor, ty: Tensor, tx: Tensor, shape: Tuple[int, int, 
     return cx * (qx - tx.reshape(1, -1)) ** 2 + cy * (qy - ty.reshape(1, -1)) ** 2 + cz * (qz - tz.reshape(1, -1)) ** 2
 
 
-def idw_exact(tz: Tensor, ty: Tensor, tx: Tensor, values: Tensor, shape: Tuple[int, int, int], k: int = 4,
-              tau: float = 0.05, chunk: int = 8192, return_neighbors: bool = False):
-    """IDW with exact integer ordering and the deterministic tie rule *smaller point index wins*.
-
-    This is the behaviour the CUDA kernel implements (SURVEY.md 8c protocol).  Distances are
-    evaluated in fp32 from the integer key: d = sqrt(key) / ((W-1)(H-1)(D-1)).
-    """
+def idw_exact_table(tz: Tensor, ty: Tensor, tx: Tensor, shape: Tuple[int, int, int], k: int = 4, tau: float = 0.05,
+                    chunk: int = 8192):
+    """Neighbour indices [Q,kk] (int64 tensor) and normalised weights [Q,kk] (numpy float32) of ``idw_exact``: they depend on
+    the point positions only, so samples that share a gauge pattern (the 'stis' mask) share the table."""
     D, H, W = shape
     Q, N = D * H * W, tz.numel()
     kk = min(k, N)
     sw, sh, sd = max(W - 1, 1), max(H - 1, 1), max(D - 1, 1)
     cx, cy, cz = (sh * sd) ** 2, (sw * sd) ** 2, (sw * sh) ** 2
     denom = float(sw * sh * sd)
-    outs = []
-    nb = torch.empty(Q, kk, dtype=torch.int64) if return_neighbors else None
     q = torch.arange(Q)
     qz, qy, qx = q // (H * W), (q // W) % H, q % W
-    values_np = values.detach().to(torch.float32).contiguous().numpy()
+    nb = torch.empty(Q, kk, dtype=torch.int64)
+    wt = np.empty((Q, kk), dtype=np.float32)
     for s in range(0, Q, chunk):
         e = min(s + chunk, Q)
         key = (cx * (qx[s:e, None] - tx[None]) ** 2 + cy * (qy[s:e, None] - ty[None]) ** 2
@@ -135,21 +131,32 @@ def idw_exact(tz: Tensor, ty: Tensor, tx: Tensor, values: Tensor, shape: Tuple[i
         # stable ordering on (key, index): index < 2^20 always holds for our sizes
         comp = key * (1 << 20) + torch.arange(N)[None]
         ck, _ = torch.topk(comp, kk, dim=1, largest=False)
-        ik = ck & ((1 << 20) - 1)
+        nb[s:e] = ck & ((1 << 20) - 1)
         # The fp32 weight arithmetic runs in numpy (single-threaded): torch's multi-threaded CPU elementwise/reduction
         # path was observed to be irreproducible run-to-run (3e-5) on the GPU boxes' 16-core hosts.
-        ck_np, ik_np = ck.numpy(), ik.numpy()
-        dk = np.sqrt((ck_np >> 20).astype(np.float32)) / np.float32(denom)
+        dk = np.sqrt((ck.numpy() >> 20).astype(np.float32)) / np.float32(denom)
         inv = np.float32(1.0) / (dk + np.float32(tau))
         w = inv * inv
-        w = w / (w.sum(axis=1, keepdims=True, dtype=np.float32) + np.float32(1e-12))
-        if values.requires_grad:       # autograd path (training-step oracle): linear in `values`
-            outs.append((values[ik] * torch.from_numpy(w)).sum(dim=1))
-        else:
-            outs.append(torch.from_numpy((values_np[ik_np] * w).sum(axis=1, dtype=np.float32)))
-        if nb is not None:
-            nb[s:e] = ik
-    out = torch.cat(outs).reshape(D, H, W)
+        wt[s:e] = w / (w.sum(axis=1, keepdims=True, dtype=np.float32) + np.float32(1e-12))
+    return nb, wt
+
+
+def idw_exact(tz: Tensor, ty: Tensor, tx: Tensor, values: Tensor, shape: Tuple[int, int, int], k: int = 4,
+              tau: float = 0.05, chunk: int = 8192, return_neighbors: bool = False, table=None):
+    """IDW with exact integer ordering and the deterministic tie rule *smaller point index wins*.
+
+    This is the behaviour the CUDA kernel implements (SURVEY.md 8c protocol).  Distances are
+    evaluated in fp32 from the integer key: d = sqrt(key) / ((W-1)(H-1)(D-1)).
+    ``table`` = a precomputed ``idw_exact_table`` of the same points (optional).
+    """
+    D, H, W = shape
+    nb, wt = table if table is not None else idw_exact_table(tz, ty, tx, shape, k, tau, chunk)
+    if values.requires_grad:       # autograd path (training-step oracle): linear in `values`
+        out = (values[nb] * torch.from_numpy(wt)).sum(dim=1)
+    else:
+        values_np = values.detach().to(torch.float32).contiguous().numpy()
+        out = torch.from_numpy((values_np[nb.numpy()] * wt).sum(axis=1, dtype=np.float32))
+    out = out.reshape(D, H, W)
     return (out, nb) if return_neighbors else out
 
 
@@ -211,6 +218,7 @@ def input_block(sd: State, masked: Tensor, masks: Tensor, k: int = 4, tau: float
     B, D, H, W = masked.shape
     proc = gated_frames(sd, masked)
     outs = []
+    tables = {}                      # neighbour tables of this call, keyed by the point pattern (shared by 'stis' batches)
     for b in range(B):
         tz, ty, tx = observed_points(masks[b])
         if tz.numel() == 0:
@@ -218,7 +226,10 @@ def input_block(sd: State, masked: Tensor, masks: Tensor, k: int = 4, tau: float
             continue
         vals = proc[b][tz, ty, tx]
         if idw == "exact":
-            outs.append(idw_exact(tz, ty, tx, vals, (D, H, W), k, tau))
+            pk = (tz.numpy().tobytes(), ty.numpy().tobytes(), tx.numpy().tobytes())
+            if pk not in tables:
+                tables[pk] = idw_exact_table(tz, ty, tx, (D, H, W), k, tau)
+            outs.append(idw_exact(tz, ty, tx, vals, (D, H, W), k, tau, table=tables[pk]))
         else:
             pts = torch.stack([tx.float() / max(W - 1, 1), ty.float() / max(H - 1, 1), tz.float() / max(D - 1, 1)],
                               dim=-1)
@@ -541,8 +552,10 @@ def adam_step(params: Dict[str, Tensor], grads: Dict[str, Tensor], state: Dict[s
 
 def gan_train_step(g_sd: Dict[str, Tensor], d_sd: Dict[str, Tensor], frames: Tensor, masked: Tensor, masks: Tensor,
                    opt_g: Dict, opt_d: Dict, step: int, k1_weight: float = 0.05, adv_weight: float = 0.01,
-                   lr: float = 1e-4, beta1: float = 0.0, beta2: float = 0.99, idw: str = "exact") -> Dict[str, float]:
-    """One iteration in the reference trainer's order (hinge loss).  Mutates g_sd/d_sd/optimizer state."""
+                   lr: float = 1e-4, beta1: float = 0.0, beta2: float = 0.99, idw: str = "exact",
+                   grads_out: Optional[Dict] = None) -> Dict[str, float]:
+    """One iteration in the reference trainer's order (hinge loss).  Mutates g_sd/d_sd/optimizer state.
+    grads_out (optional dict) receives {"g": {name: grad}, "d": {name: grad}, "preds": generator output} of this step."""
     g_train = [k for k in g_sd if not k.endswith(G_FROZEN_SUFFIX)]
     d_train = [k for k in d_sd if k.endswith("weight_orig") or k.endswith("bias") or k.startswith("alpha")]
     gp = {k: (g_sd[k].detach().clone().requires_grad_(True) if k in g_train else g_sd[k]) for k in g_sd}
@@ -567,6 +580,8 @@ def gan_train_step(g_sd: Dict[str, Tensor], d_sd: Dict[str, Tensor], frames: Ten
     adv = gan_loss(lg, True, "hinge", False) * adv_weight
     total = loss_g + adv
     gg = torch.autograd.grad(total, [gp[k] for k in g_train], allow_unused=True)
+    if grads_out is not None:
+        grads_out["g"], grads_out["d"], grads_out["preds"] = dict(zip(g_train, gg)), dict(zip(used, gd)), preds.detach()
     adam_step(g_sd, dict(zip(g_train, gg)), opt_g, step, lr, beta1, beta2)
     return {"rec": float(loss_g.detach()), "pool": parts["pool"], "reg": parts["reg"], "adv": float(adv.detach()),
             "dis": float(loss_d.detach()), "total": float(total.detach())}

@@ -9,6 +9,9 @@ namespace p2i {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+static thread_local int g_last_variant = 0;
+void set_last_variant(int code) { g_last_variant = code; }
+int last_variant() { return g_last_variant; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -81,4 +84,5 @@ extern "C" {
 int p2i_abi_version(void) { return 1; }
 const char* p2i_last_error(void) { return p2i::g_err; }
 long long p2i_launch_count(void) { return p2i::g_launches.load(); }
+int p2i_conv_last_variant(void) { return p2i::last_variant(); }
 }

@@ -40,4 +40,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 int sm_count();
 
+// Debug record of the kernel variant the calling thread launched last (p2i_conv_last_variant; tests assert that the
+// instantiation under test is the one the benchmark runs).
+void set_last_variant(int code);
+
 }  // namespace p2i

@@ -392,6 +392,7 @@ static int run_igemm(const void* x, const void* w, const P2iConvDesc& d, const v
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
+    set_last_variant(1000000 + NT * 100);
     if (NT == 256) return launch_conv<256>(tmA, tmB, p, st);
     if (NT == 128) return launch_conv<128>(tmA, tmB, p, st);
     return launch_conv<64>(tmA, tmB, p, st);

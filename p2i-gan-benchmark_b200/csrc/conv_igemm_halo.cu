@@ -666,7 +666,11 @@ int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const voi
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
-#define HALO_LAUNCH(NT_, RES_, CG_) return launch_halo<NT_, RES_, CG_>(tmA, tmB, tmO, tmX, p, smem_bytes, st)
+#define HALO_LAUNCH(NT_, RES_, CG_)                                                          \
+    do {                                                                                     \
+        set_last_variant(2000000 + p.MB * 100000 + NT_ * 100 + (RES_ ? 10 : 0) + CG_);       \
+        return launch_halo<NT_, RES_, CG_>(tmA, tmB, tmO, tmX, p, smem_bytes, st);           \
+    } while (0)
     if (CG == 2) {
         if (NT == 256) { if (res) HALO_LAUNCH(256, true, 2); else HALO_LAUNCH(256, false, 2); }
         if (NT == 128) { if (res) HALO_LAUNCH(128, true, 2); else HALO_LAUNCH(128, false, 2); }

@@ -409,6 +409,7 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
                 if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_wgrad2 smem attribute: %s", cudaGetErrorString(e));
                 configured2 = true;
             }
+            set_last_variant(4000000 + q.mode);
             conv_wgrad2_kernel<<<items * ks, 256, WG2_SMEM, as_stream(stream)>>>(tmX, tmY, q);
             P2I_CHECK_LAUNCH("conv_wgrad2_kernel");
             return P2I_OK;
@@ -458,6 +459,7 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
         if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_wgrad smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
+    set_last_variant(3000000 + p.nt * 100 + (p.stacked ? 10 : 0));
     conv_wgrad_kernel<<<items * ks, 256, WG_SMEM, as_stream(stream)>>>(tmX, tmY, p);
     P2I_CHECK_LAUNCH("conv_wgrad_kernel");
     return P2I_OK;

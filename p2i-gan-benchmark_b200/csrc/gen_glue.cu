@@ -301,3 +301,69 @@ extern "C" int p2i_window_blend(const float* preds, float* out, int L, int HW, i
     P2I_CHECK_LAUNCH("window_blend_kernel");
     return P2I_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone DownsampleDuplicateChannels (layer.py:205-214) on the reference's own NCHW f32 layout: max_pool2d(2,2), then
+// view [B*T, C/T] -> repeat_interleave(2, dim=1) -> view [B, 2C], i.e. input channel c feeds output channels 2c and 2c+1.
+// The generator never calls this (its three levels are fused into pyramid_fwd/bwd); it exists so that the module's own
+// forward/backward work as in the reference.  HBM-bound: 4 B read + 2 B written per input pixel.
+namespace p2i {
+__global__ void __launch_bounds__(256) downsample_dup_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                 long long n_out, int C, int h, int w) {
+    // one thread per (b, c, yo, xo): reads a 2x2 window, writes the two duplicate channels
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int xo = static_cast<int>(i % w);
+    const int yo = static_cast<int>((i / w) % h);
+    const long long bc = i / (static_cast<long long>(w) * h);
+    const int c = static_cast<int>(bc % C);
+    const long long b = bc / C;
+    const float2* r0 = reinterpret_cast<const float2*>(x + ((bc * 2 * h + 2 * yo) * 2 * w + 2 * xo));
+    const float2* r1 = reinterpret_cast<const float2*>(x + ((bc * 2 * h + 2 * yo + 1) * 2 * w + 2 * xo));
+    const float2 a = __ldg(r0), d = __ldg(r1);
+    const float m = fmaxf(fmaxf(a.x, a.y), fmaxf(d.x, d.y));
+    const long long o = ((b * 2 * C + 2 * c) * h + yo) * w + xo;
+    y[o] = m;
+    y[o + static_cast<long long>(h) * w] = m;
+}
+
+__global__ void __launch_bounds__(256) downsample_dup_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ dx, long long n_out, int C, int h, int w) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int xo = static_cast<int>(i % w);
+    const int yo = static_cast<int>((i / w) % h);
+    const long long bc = i / (static_cast<long long>(w) * h);
+    const int c = static_cast<int>(bc % C);
+    const long long b = bc / C;
+    const long long i0 = (bc * 2 * h + 2 * yo) * 2 * w + 2 * xo, i1 = i0 + 2 * w;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(x + i0)), d = __ldg(reinterpret_cast<const float2*>(x + i1));
+    const long long o = ((b * 2 * C + 2 * c) * h + yo) * w + xo;
+    const float g = dy[o] + dy[o + static_cast<long long>(h) * w];
+    // max_pool2d backward: the FIRST maximum in window scan order receives the gradient (NaN counts as maximal, as in ATen)
+    float m = a.x; int k = 0;
+    if (a.y > m || a.y != a.y) { m = a.y; k = 1; }
+    if (d.x > m || d.x != d.x) { m = d.x; k = 2; }
+    if (d.y > m || d.y != d.y) { m = d.y; k = 3; }
+    *reinterpret_cast<float2*>(dx + i0) = make_float2(k == 0 ? g : 0.f, k == 1 ? g : 0.f);
+    *reinterpret_cast<float2*>(dx + i1) = make_float2(k == 2 ? g : 0.f, k == 3 ? g : 0.f);
+}
+}  // namespace p2i
+
+extern "C" int p2i_downsample_dup_fwd(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+    P2I_CHECK_ARG(x && y, "downsample_dup_fwd: null pointer");
+    P2I_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "downsample_dup_fwd: H=%d W=%d must be even", H, W);
+    const long long n = static_cast<long long>(B) * C * (H / 2) * (W / 2);
+    p2i::downsample_dup_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, p2i::as_stream(stream)>>>(x, y, n, C, H / 2, W / 2);
+    P2I_CHECK_LAUNCH("downsample_dup_fwd_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_downsample_dup_bwd(const float* x, const float* dy, float* dx, int B, int C, int H, int W, void* stream) {
+    P2I_CHECK_ARG(x && dy && dx, "downsample_dup_bwd: null pointer");
+    P2I_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "downsample_dup_bwd: H=%d W=%d must be even", H, W);
+    const long long n = static_cast<long long>(B) * C * (H / 2) * (W / 2);
+    p2i::downsample_dup_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, p2i::as_stream(stream)>>>(x, dy, dx, n, C, H / 2, W / 2);
+    P2I_CHECK_LAUNCH("downsample_dup_bwd_kernel");
+    return P2I_OK;
+}

@@ -161,6 +161,72 @@ __global__ void metrics_finalize_kernel(double* __restrict__ acc, float* __restr
     if (i < 50) acc[i] = 0.0;       // scratch is left clean for the next update
 }
 
+// FSS for one (threshold, box size k <= 32): separable box sums of the two exceedance masks through shared memory.
+constexpr int FT = 32;                 // output tile edge
+constexpr int FSM = FT + 31;           // staged edge for k = 32
+__global__ void __launch_bounds__(256) fss_generic_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                          double* __restrict__ acc, int N, int H, int W, float thr, int k) {
+    __shared__ unsigned char sp[FSM * FSM], st[FSM * FSM];
+    __shared__ unsigned short hp[FSM * FT], ht[FSM * FT];
+    __shared__ float red[8][2];
+    const int n = blockIdx.z;
+    const int pad = k >> 1;
+    const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+    const int oy0 = blockIdx.y * FT, ox0 = blockIdx.x * FT;
+    const int S = FT + k - 1;
+    const float* P = pred + static_cast<size_t>(n) * H * W;
+    const float* Tg = target + static_cast<size_t>(n) * H * W;
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        const int sy = e / S, sx = e - sy * S;
+        const int y = oy0 - pad + sy, x = ox0 - pad + sx;
+        unsigned char a = 0, b = 0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            a = rain(P[static_cast<size_t>(y) * W + x]) >= thr;
+            b = rain(Tg[static_cast<size_t>(y) * W + x]) >= thr;
+        }
+        sp[sy * FSM + sx] = a;
+        st[sy * FSM + sx] = b;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S * FT; e += blockDim.x) {      // horizontal box sums
+        const int sy = e / FT, tx = e - sy * FT;
+        int a = 0, b = 0;
+        for (int d = 0; d < k; ++d) { a += sp[sy * FSM + tx + d]; b += st[sy * FSM + tx + d]; }
+        hp[sy * FT + tx] = static_cast<unsigned short>(a);
+        ht[sy * FT + tx] = static_cast<unsigned short>(b);
+    }
+    __syncthreads();
+    float num = 0.f, den = 0.f;
+    const float inv = 1.f / static_cast<float>(k * k);
+    for (int e = threadIdx.x; e < FT * FT; e += blockDim.x) {
+        const int ty = e / FT, tx = e - ty * FT;
+        if (oy0 + ty >= Ho || ox0 + tx >= Wo) continue;
+        int a = 0, b = 0;
+        for (int d = 0; d < k; ++d) { a += hp[(ty + d) * FT + tx]; b += ht[(ty + d) * FT + tx]; }
+        const float fa = static_cast<float>(a) * inv, fb = static_cast<float>(b) * inv;
+        num += (fa - fb) * (fa - fb);
+        den += fa * fa + fb * fb;
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = num; red[warp][1] = den; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float r = 0.f;
+        for (int w8 = 0; w8 < 8; ++w8) r += red[w8][threadIdx.x];
+        if (r != 0.f) atomicAdd(&acc[threadIdx.x], static_cast<double>(r));
+    }
+}
+
+__global__ void fss_generic_finalize_kernel(double* __restrict__ acc, float* __restrict__ state, double cnt) {
+    const float num = static_cast<float>(acc[0] / cnt), den = static_cast<float>(acc[1] / cnt);
+    state[0] += 1.0f - num / (den + 1e-10f);
+    state[1] += 1.0f;
+    acc[0] = 0.0;
+    acc[1] = 0.0;
+}
+
 }  // namespace p2i
 
 using namespace p2i;
@@ -181,5 +247,20 @@ extern "C" int p2i_metrics_update(const float* pred, const float* target, int N,
     P2I_CHECK_LAUNCH("metrics_kernel");
     metrics_finalize_kernel<<<1, 64, 0, as_stream(stream)>>>(scratch, state, p);
     P2I_CHECK_LAUNCH("metrics_finalize_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_fss_update(const float* pred, const float* target, int N, int H, int W, float threshold, int scale,
+                              double* scratch, float* state, void* stream) {
+    P2I_CHECK_ARG(pred && target && scratch && state, "fss_update: null pointer");
+    P2I_CHECK_ARG(scale >= 1 && scale <= 32, "fss_update: box size %d outside 1..32", scale);
+    P2I_CHECK_ARG(N >= 1 && N <= 65535, "fss_update: N = %d outside 1..65535 (split the batch)", N);
+    const int pad = scale / 2;
+    const int Ho = H + 2 * pad - scale + 1, Wo = W + 2 * pad - scale + 1;
+    dim3 grid(cdiv(Wo, FT), cdiv(Ho, FT), N);
+    fss_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, target, scratch, N, H, W, threshold, scale);
+    P2I_CHECK_LAUNCH("fss_generic_kernel");
+    fss_generic_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(scratch, state, static_cast<double>(N) * Ho * Wo);
+    P2I_CHECK_LAUNCH("fss_generic_finalize_kernel");
     return P2I_OK;
 }

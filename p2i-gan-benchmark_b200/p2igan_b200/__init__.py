@@ -15,12 +15,14 @@ from .discriminator import P2IDiscriminator  # noqa: F401
 from .generator import P2IGenerator  # noqa: F401
 from .infer import run_inference, sliding_window_infer  # noqa: F401
 from .losses import ReconstructionLoss, gan_loss  # noqa: F401
-from .metrics import MetricConfig, RainfallMetricSuite, transform  # noqa: F401
+from .metrics import (CategoricalMetrics, FractionalSkillScoreMetric, MetricConfig, RainfallMetricSuite,  # noqa: F401
+                      RegressionMetrics, transform)
 from .optim import FusedAdam  # noqa: F401
 from .registry import build_discriminator, build_generator  # noqa: F401
 from .train_step import FlatGrads, GANTrainStep, GraphedDPStep, GraphedStep  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 
 __all__ = ["P2IGenerator", "P2IDiscriminator", "build_generator", "build_discriminator", "ReconstructionLoss", "gan_loss",
-           "MetricConfig", "RainfallMetricSuite", "transform", "FusedAdam", "GANTrainStep", "GraphedStep", "FlatGrads",
+           "MetricConfig", "RainfallMetricSuite", "RegressionMetrics", "CategoricalMetrics", "FractionalSkillScoreMetric",
+           "transform", "FusedAdam", "GANTrainStep", "GraphedStep", "FlatGrads",
            "GraphedDPStep", "sliding_window_infer", "run_inference", "Trainer", "prepare_batch", "prepare_batch_u8", "set_stream_overlap"]

@@ -158,15 +158,31 @@ class EBlock(nn.Module):
 
 class DownsampleDuplicateChannels(nn.Module):
     """max-pool 2x2 + duplicate every channel (reference: layer.py:200-214).  Parameter-free; the
-    generator fuses the three levels it needs into one kernel (ops.pyramid_fwd)."""
+    generator fuses the three levels it needs into one kernel (ops.pyramid_fwd); the module's own forward runs one level."""
 
     def __init__(self, length):
         super().__init__()
         self.t = length
 
     def forward(self, x):
-        raise RuntimeError("DownsampleDuplicateChannels is fused into P2IGenerator.forward (ops.pyramid_fwd); "
-                           "it has no standalone kernel")
+        """x [B,C,H,W] f32 -> [B,2C,H/2,W/2] (one level; differentiable).  Same checks as the reference (:207-208)."""
+        require_cuda(x)
+        b, c, h, w = x.shape
+        if c % self.t != 0:
+            raise ValueError(f"Channel dimension {c} must be divisible by length {self.t}.")
+        return _DownsampleDupFn.apply(x.contiguous().float())
+
+
+class _DownsampleDupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.downsample_dup_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.downsample_dup_bwd(x, dy.contiguous().float())
 
 
 class AttentionBlock(nn.Module):

@@ -156,6 +156,23 @@ def pyramid_fwd(stem: Tensor):
     return x4, x8
 
 
+def downsample_dup_fwd(x: Tensor) -> Tensor:
+    """x [B,C,H,W] f32 -> [B,2C,H/2,W/2] f32: max_pool2d(2,2) + channel duplication (layer.py:205-214)."""
+    require_cuda(x)
+    B, C, H, W = x.shape
+    y = torch.empty(B, 2 * C, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    LIB.call("p2i_downsample_dup_fwd", ptr(_chk(x, torch.float32, "x")), ptr(y), B, C, H, W, stream())
+    return y
+
+
+def downsample_dup_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    LIB.call("p2i_downsample_dup_bwd", ptr(_chk(x, torch.float32, "x")), ptr(_chk(dy, torch.float32, "dy")), ptr(dx), B, C, H, W,
+             stream())
+    return dx
+
+
 def upmod_fwd(z: Tensor, pos: Tensor, bias: Tensor, skip: Optional[Tensor] = None) -> Tensor:
     B, h, w, C = z.shape
     out = torch.empty(B, 2 * h, 2 * w, C, dtype=torch.bfloat16, device=z.device)

@@ -16,18 +16,20 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
         self._stepbufs = {}
+        self._seeded = set()          # groups whose device step counter already reflects the (possibly loaded) state
 
     def _init_state(self, gi, group):
-        plist = [p for p in group["params"] if p.requires_grad or p.grad is not None]
+        # like torch.optim.Adam, state exists only for parameters that have received a gradient (the discriminator's
+        # unused `alpha3d`, models/p2igan.py:145, stays in the param group without state -- same indices as the reference)
+        plist = [p for p in group["params"] if p.grad is not None]
         dev = plist[0].device
         # one device buffer per group: [step, lr/(1-b1^t), 1/sqrt(1-b2^t), pad]; every state["step"] is a 0-dim view of [0]
         buf = self._stepbufs.get(gi)
         if buf is None or buf.device != dev:
             buf = torch.zeros(4, dtype=torch.float32, device=dev)
             self._stepbufs[gi] = buf
-            seeded = False
-        else:
-            seeded = True
+            self._seeded.discard(gi)
+        seeded = gi in self._seeded
         step = buf[0]
         for p in plist:
             st = self.state[p]
@@ -40,9 +42,38 @@ class FusedAdam(torch.optim.Optimizer):
                     buf[0] = st["step"].to(dev, torch.float32)
                     seeded = True
                 st["step"] = step
+        self._seeded.add(gi)
+
+    def state_dict(self):
+        """torch.optim.Adam's layout with an independent host scalar per ``step`` (ours are views of one device counter; a
+        checkpoint must load into the reference's Adam, scripts/train.py:125-136, whose foreach update increments each
+        step tensor separately).  Host synchronisation: checkpoints are written outside the hot loop."""
+        sd = super().state_dict()
+        host_step = {}                        # one D2H read per device counter
+        state = {}
+        for k, st in sd["state"].items():     # the packed per-parameter dicts ARE the live ones: copy before editing
+            st = dict(st)
+            if "step" in st and torch.is_tensor(st["step"]):
+                ptr_ = st["step"].data_ptr()
+                if ptr_ not in host_step:
+                    host_step[ptr_] = st["step"].detach().to("cpu", torch.float32)
+                st["step"] = host_step[ptr_].clone()
+            state[k] = st
+        sd["state"] = state
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """Also valid on an optimiser that has already stepped: the loaded moments replace the tensors the device work table
+        points to and the loaded step count replaces the device counter."""
+        super().load_state_dict(state_dict)
+        self._tables.clear()
+        self._seeded.clear()
+        for buf in self._stepbufs.values():
+            buf.zero_()
 
     def _table(self, gi, plist):
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in plist)
         tb = self._tables.get(gi)
         if tb is None or tb[0] != key:
             chunk = LIB.load().p2i_adam_chunk_elems()

@@ -96,7 +96,10 @@ class GANTrainStep:
         self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
         self.opt_d = None
         if self.use_gan:
-            self.opt_d = FusedAdam(self.flat_d.params, lr=oc["lr"], betas=betas)
+            # the optimiser sees ALL discriminator parameters in registration order, alpha3d included (grad None: skipped by
+            # the kernel, no state) -- Adam(discriminator.parameters()) of scripts/train.py:131-136, so that `optimizer_d`
+            # of a reference checkpoint loads here and ours loads there (22 params in the group, same state indices)
+            self.opt_d = FusedAdam(list(discriminator.parameters()), lr=oc["lr"], betas=betas)
             from . import disc_bwd
             disc_bwd.prepare(discriminator)
 

@@ -67,7 +67,7 @@ def test_metric_suite_stress_256_and_properties():
     for t in range(4):
         assert float(st[3 + 4 * t:7 + 4 * t].sum()) == 8 * 20 * 256 * 256
     with pytest.raises(ValueError):
-        RainfallMetricSuite(MetricConfig(scales=(1, 3)))
+        RainfallMetricSuite(MetricConfig(scales=(1, 33)))          # box sizes 1..32 (documented in INTEGRATION.md 5)
 
 
 def test_ssim_matches_oracle_restatement_and_small_images():
@@ -110,3 +110,59 @@ def test_categorical_scores_cross_check_against_exp1_golden():
     for thr, key in ((0.5, "CAT_0.5"), (2.0, "CAT_2"), (4.0, "CAT_4"), (8.0, "CAT_8")):
         for ours_k, ref_k in (("pod", "POD"), ("far", "FAR"), ("csi", "CSI")):
             assert abs(m[f"cat_thr{thr:.2f}/{ours_k}"] - ref[key][ref_k]) < 1e-5, (thr, ours_k)
+
+
+def test_arbitrary_thresholds_and_scales_and_the_three_metric_classes():
+    """MetricConfig takes any thresholds / box sizes in the reference (metric.py:186-191): six thresholds (two fused passes)
+    and box sizes outside {1,2,4,8} (generic kernel) vs the oracle; RegressionMetrics / CategoricalMetrics /
+    FractionalSkillScoreMetric (metric.py:232-239 __all__) report the same values as the suite."""
+    from p2igan_b200.metrics import (CategoricalMetrics, FractionalSkillScoreMetric, MetricConfig, RainfallMetricSuite,
+                                     RegressionMetrics)
+    thr, scales = (0.1, 0.5, 1.0, 2.0, 4.0, 8.0), (1, 3, 5, 8, 16)
+    g = torch.Generator().manual_seed(12)
+    shape = (2, 5, 1, 48, 72)
+    pred = torch.rand(shape, generator=g) ** 2 * 85.0
+    tgt = torch.rand(shape, generator=g) ** 2 * 85.0
+    ref = O.MetricSuiteOracle(thresholds=thr, scales=scales, with_ssim=True)
+    suite = RainfallMetricSuite(MetricConfig(thresholds=thr, scales=scales)).to(DEV)
+    reg, cat, fss = RegressionMetrics().to(DEV), CategoricalMetrics(thr).to(DEV), FractionalSkillScoreMetric(thr, scales).to(DEV)
+    for a, b in ((pred, tgt), (tgt.flip(-2), tgt)):
+        ref.update(a, b)
+        for m in (suite, reg, cat, fss):
+            m.update(a.to(DEV), b.to(DEV))
+    want, got = ref.compute(), suite.compute()
+    assert list(got) == list(want)                      # same keys in the reference's order (regression, categorical, FSS)
+    assert len(got) == 3 + 4 * len(thr) + len(thr) * len(scales)
+    _compare(got, want)
+    parts = {}
+    for m in (reg, cat, fss):
+        parts.update(m.compute())
+    assert parts == got
+    fss.reset()
+    assert fss.compute() == {}                          # counts == 0 -> key omitted (metric.py:178-179)
+
+
+def test_downsample_duplicate_channels_standalone_forward_backward():
+    """DownsampleDuplicateChannels.forward (layer.py:205-214) as a module of its own: values and gradient vs torch."""
+    import torch.nn.functional as F
+    from p2igan_b200.layers import DownsampleDuplicateChannels
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 24, 40, generator=g)
+    m = DownsampleDuplicateChannels(length=16)
+
+    def ref_fn(t):
+        b, c, h, w = t.shape
+        p = F.max_pool2d(t, 2, 2).view(b * 16, c // 16, h // 2, w // 2)
+        return p.repeat_interleave(2, dim=1).view(b, 2 * c, h // 2, w // 2)
+
+    xr = x.clone().requires_grad_(True)
+    yr = ref_fn(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xc = x.to(DEV).requires_grad_(True)
+    y = m(xc)
+    y.backward(gy.to(DEV))
+    assert torch.equal(y.detach().cpu(), yr.detach())
+    assert torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-6)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 24, 8, 8, device=DEV))

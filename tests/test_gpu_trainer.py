@@ -114,3 +114,46 @@ def test_graphed_trainer_and_validation_loss():
     ref /= len(val)
     assert abs(got - ref) < 3e-2 * abs(ref) + 1e-4, (got, ref)
     assert g.generator.training
+
+
+def test_load_checkpoint_into_a_live_trainer_and_reference_optimizer_state(tmp_path):
+    """(1) load_checkpoint on a trainer that has ALREADY stepped must take effect -- the fused Adam kernel's device
+    table points at the loaded moments and its device step counter is re-seeded (2 steps + save, 2 more steps, load, 1 step
+    == 3 uninterrupted steps); (2) `optimizer_d` written by torch.optim.Adam(D.parameters()) -- 22 entries incl. the unused
+    alpha3d, the reference's layout (scripts/train.py:131-136) -- loads, and our checkpoint loads into torch's Adam."""
+    from p2igan_b200 import Trainer
+    cfg = synth.make_cfg(32, 32)
+    cfg["train"]["log_step"] = 1
+    cfg["train"]["optimizer"]["lr"] = 1e-6        # see _LR_NOTE
+    data = _batches(4, 300)
+    a = Trainer(cfg, use_graphs=False)
+    a.train_epoch(data[:3])
+    b = Trainer(cfg, use_graphs=False)
+    b.train_epoch(data[:2])
+    path = tmp_path / "latest.pth"
+    b.save_checkpoint(path, epoch=1)
+    b.train_epoch([data[3], data[3]])             # wander off: parameters, moments and step counters all change
+    b.load_checkpoint(path)                       # ... and come back, on the live optimiser
+    assert b.global_step == 2
+    b.train_epoch(data[2:3])
+    for k, v in a.generator.state_dict().items():
+        assert float((v - b.generator.state_dict()[k]).abs().max()) <= 3e-5, k
+    for k, v in a.discriminator.state_dict().items():
+        assert float((v - b.discriminator.state_dict()[k]).abs().max()) <= 3e-5, k
+    assert float(next(iter(b.opt_g.state.values()))["step"]) == 3.0
+    assert float(next(iter(b.opt_d.state.values()))["step"]) == 3.0
+    # reference-side optimiser state
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    assert len(ck["optimizer_d"]["param_groups"][0]["params"]) == 22 and 1 not in ck["optimizer_d"]["state"]
+    ref_opt = torch.optim.Adam([p.detach().cpu().requires_grad_(True) for p in b.discriminator.parameters()], lr=1e-4,
+                               betas=(0.0, 0.99))
+    ref_opt.load_state_dict(ck["optimizer_d"])
+    sd = ref_opt.state_dict()
+    c = Trainer(cfg, use_graphs=False)
+    c.opt_d.load_state_dict(sd)                   # torch.optim.Adam -> FusedAdam
+    c.opt_g.load_state_dict(ck["optimizer_g"])
+    c.generator.load_state_dict(ck["generator"]); c.discriminator.load_state_dict(ck["discriminator"])
+    c.global_step = 2
+    c.train_epoch(data[2:3])
+    for k, v in a.discriminator.state_dict().items():
+        assert float((v - c.discriminator.state_dict()[k]).abs().max()) <= 3e-5, k

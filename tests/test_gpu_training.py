@@ -147,7 +147,7 @@ def _grads_oracle(sd, masked, masks, frames, k1):
     return float(loss), dict(zip(train, g)), out.detach()
 
 
-@pytest.mark.parametrize("H,W,B,n_obs", [(32, 32, 2, 12), (64, 64, 1, 30)])
+@pytest.mark.parametrize("H,W,B,n_obs", [(32, 32, 2, 12), (64, 64, 1, 30), (128, 128, 1, 79)])
 def test_generator_gradients_match_oracle_autograd(H, W, B, n_obs):
     from p2igan_b200 import build_generator
     from p2igan_b200.losses import ReconstructionLoss
@@ -200,8 +200,12 @@ def test_fused_adam_matches_torch_adam():
 
 def test_gan_train_step_matches_oracle_and_reference_golden(golden):
     """Two full G+D iterations (B=2, 32x32) in train.py's order vs the oracle step and the reference's own losses.
-    Losses are fp32 reductions of bf16-path activations: rel 3e-2 (rec/dis/adv). Parameters after 2 Adam steps move
-    by ~lr=1e-4 per element: compare the UPDATE direction via the oracle's parameters, abs 2.5e-4."""
+    Loss gate vs the oracle (same IDW tie rule): rel 1e-2, SURVEY.md 8c.  Yardstick (tests/tools/bf16_loss_yardstick.py: the
+    oracle's own step under torch bf16 autocast vs fp32, this configuration): rec 1.4e-4, pool 4.7e-4, reg 2.8e-4, dis
+    3.0e-3; adv (|value| ~3.5e-4) moves by 9e-6 absolute.  The reference GOLDEN was produced with the reference's own IDW
+    tie resolution (cdist rounding + topk order), which changes ~20 % of the interpolated pixels: that
+    comparison keeps a 6e-2 gate (the two CPU tie rules differ from each other by up to 4e-2 on these losses).
+    Parameters after 2 Adam steps move by ~lr=1e-4 per element: compare the UPDATE direction via the oracle's parameters."""
     from p2igan_b200 import build_discriminator, build_generator
     from p2igan_b200.train_step import GANTrainStep
     cfg = synth.make_cfg(32, 32)
@@ -220,7 +224,7 @@ def test_gan_train_step_matches_oracle_and_reference_golden(golden):
         ref = O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it + 1, idw="exact")
         gold = golden["train32"]["steps"][it]
         for k in ("rec", "pool", "dis"):
-            assert abs(ours[k] - ref[k]) < 3e-2 * abs(ref[k]) + 1e-4, (it, k, ours[k], ref[k])
+            assert abs(ours[k] - ref[k]) < 1e-2 * abs(ref[k]) + 1e-4, (it, k, ours[k], ref[k])
             assert abs(ours[k] - gold[k]) < 6e-2 * abs(gold[k]) + 1e-4, (it, k, ours[k], gold[k])
         assert abs(ours["adv"] - ref["adv"]) < 2e-3, (it, ours["adv"], ref["adv"])
     # Adam with beta1 = 0 takes ~lr-sized sign-like steps, so elements whose gradient is at the bf16 noise floor may
