@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the P2I-GAN hot path on B200 (contract: see the task's bench section).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|infer|gauge1pct|stress256] [--impl ours|reference]
 
-N=1 default workload: BASELINE.json configs[1] -- generator-only inference, batch 32 synthetic
-radar-input events of 16x128x128, random-init weights (seed 2024), 79 gauge pixels.
-One "step" = one pass of the hot path over one batch.  Prints ONE JSON line on rank 0.
+Default workload: BASELINE.json configs[2] -- full GAN training step, batch 16/GPU, 16x128x128 synthetic events, 79 gauge
+pixels, random-init weights (seed 2024); `metric` is quoted on it.  One "step" = one pass of the hot path over one batch.
+Prints ONE JSON line on rank 0.
 
-  value        events/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e          events/s through the public module API with pinned HOST buffers: H2D of the step's
-               inputs and D2H of the step's result inside the timed region
-  roofline     dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs / CUDA-event time
-               of its launches, against MEASURED_PEAKS.json
-  cpu_baseline the oracle (CPU restatement of the reference, oracle/) timed on this box's host cores
-               on a bounded sample of the same workload
+  value        events/s with inputs resident in HBM (CUDA events around exactly K steps, max over ranks)
+  e2e          events/s through the public module API with pinned HOST buffers: H2D of the step's inputs and D2H of the
+               step's result inside the timed region
+  roofline     dominant kernels (tcgen05 implicit-GEMM conv forward/dgrad; wgrad): algorithmic FLOPs / CUDA-event time of
+               their launches against MEASURED_PEAKS.json (burst figure unless the timed region is >= 2 s), plus
+               `hbm_kernels`: every bandwidth-bound entry point as achieved GB/s / measured HBM GB/s
+  sustained    the same step repeated for >= 2 s when K steps are shorter than that (clock / power response)
+  infer / gauge1pct / stress256
+               sub-records of the other BASELINE configs (configs[1], [3], [4]) measured in the same run (N = 1)
+  cpu_baseline the reference's CPU path timed on this box's host cores on a bounded sample of the same workload
 """
 from __future__ import annotations
 
@@ -40,22 +43,28 @@ import torch  # noqa: E402
 
 import synth  # noqa: E402
 
-T, H, W = 16, 128, 128
-N_OBS = 79
-G_FWD_FLOP_PER_EVENT = 39.54e9       # SURVEY.md 8d (2*MAC of the reference's conv calls)
+T = 16
 
-
-def conv_flops_fwd(B):
-    """Algorithmic FLOPs (2*MAC) of the tensor-core kernel launches in one generator forward, as executed
-    (the UPPos projection runs at low resolution: 4x fewer MACs than the reference's)."""
-    f = 0.0
-    for lvl, C in enumerate((64, 128, 256, 512)):
-        hw = (H >> lvl) * (W >> lvl)
-        f += 8 * 2.0 * B * hw * C * C * 9
-    for lvl, C in ((1, 128), (2, 256), (3, 512)):
-        hw = (H >> lvl) * (W >> lvl)
-        f += 2.0 * B * hw * C * (C // 2)
-    return f
+# name -> (metric, description, train?, batch/GPU, H = W, observed pixels, BASELINE.json configs index)
+WORKLOADS = {
+    "train": ("train events/s (G+D step, 16x128x128)",
+              "full GAN training step (generator + dual-branch patch discriminator, weighted-L1 + temporal-KL + hinge, "
+              "2x Adam) p2igan_gan_baseline.json, batch 16/GPU, synthetic events 16x128x128 (BASELINE configs[2])",
+              True, 16, 128, 79, 2),
+    "infer": ("infer events/s (generator forward, 16x128x128)",
+              "P2IGAN generator-only inference, batch 32 synthetic radar-input events 16x128x128 (BASELINE configs[1])",
+              False, 32, 128, 79, 1),
+    "gauge1pct": ("train events/s (G+D step, 16x128x128, 1 % gauges)",
+                  "gauge-input sparse-mask training: ~1 % observed pixels (164), gauge values = radar + N(0, 0.02); T=20 events are "
+                  "truncated to the model's 16 frames as the reference's loader does (sti_dataset.py:205-207; SURVEY.md 0.7), "
+                  "128x128, batch 16/GPU (BASELINE configs[3])",
+                  True, 16, 128, 164, 3),
+    "stress256": ("train events/s (G+D step, 16x256x256)",
+                  "scaled-domain stress: 256x256 synthetic events (T=20 truncated to 16 frames for training), 1 % gauges (655), "
+                  "batch 8/GPU training step; metric sweep on 8 x 20x256x256 events reported under `metrics_sweep` "
+                  "(BASELINE configs[4])",
+                  True, 8, 256, 655, 4),
+}
 
 
 class ClockSampler:
@@ -83,29 +92,34 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        """Summary of the samples taken in [t0, t1] (the sampler keeps running)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, l in self.lines:
+        sm, pw, mx, reasons = [], [], None, set()
+        for ts, l in list(self.lines):
             p = [x.strip() for x in l.split(",")]
             if len(p) < 9:
                 continue
             try:
-                if t0 - 0.05 <= ts <= t1 + 0.15:
-                    sm.append(float(p[1]))
                 mx = float(p[2])
+                if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                    continue
+                sm.append(float(p[1]))
+                pw.append(float(p[3]))
             except ValueError:
                 continue
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
 
 
 def peaks():
@@ -116,84 +130,155 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def make_inputs(name, B, HW, n_obs, seed, dev=None):
+    """(frames, masked, masks) of one batch; the gauge mask is ONE static pattern (seed 1), as the reference's 'stis' mask
+    file is (data/sti_dataset.py:104-117, SURVEY.md 8d inputs 2-4)."""
+    mask = synth.make_mask(B, T, HW, HW, n_obs, 1)
+    fr = synth.make_batch(B, T, HW, HW, n_obs, seed)[0]
+    if name == "gauge1pct":          # gauge != radar: observed values carry N(0, 0.02) noise (SURVEY.md 8d input 4)
+        g = torch.Generator().manual_seed(seed + 31)
+        masked = (fr + 0.02 * torch.randn(fr.shape, generator=g)).clamp(0, 1) * mask
+    else:
+        masked = fr * mask
+    out = (fr, masked, mask)
+    return tuple(t.to(dev) for t in out) if dev is not None else out
+
+
 # ----------------------------------------------------------------------------------------------- CPU / reference arm
-def cpu_generator_events_per_s(n_events: int, steps: int, warmup: int):
-    """Oracle (CPU restatement of the reference generator, reference-style IDW numerics) on the host cores."""
-    from oracle import p2i_oracle as O
-    from p2igan_b200 import build_generator
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    torch.manual_seed(2024)
-    sd = {k: v.detach().clone() for k, v in build_generator(synth.make_cfg(H, W)).state_dict().items()}
-    frames, masked, masks = synth.make_batch(n_events, T, H, W, N_OBS, 1)
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.generator_forward(sd, masked, masks, idw="ref")
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.generator_forward(sd, masked, masks, idw="ref")
-        dt = time.perf_counter() - t0
-    return n_events * steps / dt, cores, dt / steps
+def _reference_modules():
+    """The UNMODIFIED reference (its own nn.Modules, losses and torch.optim.Adam) when the checkout is present -- it is in
+    the build container, it is not on the GPU box -- else None."""
+    import ref_stubs
+    if not ref_stubs.reference_available():
+        return None
+    ref_stubs.install_stubs()
+    for m in [k for k in sys.modules if k == "p2igan_bench" or k.startswith("p2igan_bench.")]:
+        del sys.modules[m]
+    sys.path.insert(0, ref_stubs.REFERENCE_ROOT)
+    import p2igan_bench.models as M
+    import p2igan_bench.modules as MD
+    assert os.path.abspath(M.__file__).startswith(os.path.abspath(ref_stubs.REFERENCE_ROOT)), M.__file__
+    return M, MD
 
 
-def cpu_train_events_per_s(n_events: int, steps: int, warmup: int):
-    """Oracle GAN training step (scripts/train.py order: G fwd, rec loss, D x2, D Adam, D(G), G bwd, G Adam) on the host."""
-    from oracle import p2i_oracle as O
-    from p2igan_b200 import build_discriminator, build_generator
+def cpu_events_per_s(name: str, B: int, steps: int, warmup: int):
+    """(events/s, cores, s/step, kind) of the reference's CPU path for workload `name` on all host cores.
+    kind "reference": the reference's own modules, stepped in scripts/train.py:240-326's order (its Trainer needs a dataset
+    on disk and MLflow); kind "port": oracle/p2i_oracle.py, the CPU restatement (reference-style cdist/topk IDW)."""
+    _, _, train, _, HW, n_obs, _ = WORKLOADS[name]
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    torch.manual_seed(2024)
-    cfg = synth.make_cfg(H, W)
-    g_sd = {k: v.detach().clone() for k, v in build_generator(cfg).state_dict().items()}
-    d_sd = {k: v.detach().clone() for k, v in build_discriminator(cfg).state_dict().items()}
-    og, od = {}, {}
-    fr, mf, mk = synth.make_batch(n_events, T, H, W, N_OBS, 1)
-    it = 0
+    cfg = synth.make_cfg(HW, HW)
+    fr, mf, mk = make_inputs(name, B, HW, n_obs, 1)
+    ref = _reference_modules()
+    if ref is not None:
+        M, MD = ref
+        torch.manual_seed(2024)
+        G = M.build_generator(cfg)
+        if train:
+            D = M.build_discriminator(cfg)
+            og = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.0, 0.99))
+            od = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.99))
+            rl = MD.ReconstructionLoss(k1_alpha=cfg["loss"]["k1_weight"])
+            G.train(); D.train()
+
+            def step():
+                preds = G(mf, mk)
+                loss_g, _ = rl(preds, fr, mk)
+                for p in D.parameters():
+                    p.requires_grad_(True)
+                lf, lr_ = D(preds.detach()), D(fr)
+                loss_d = (MD.gan_loss(lr_, True, loss_type="hinge", is_disc=True)
+                          + MD.gan_loss(lf, False, loss_type="hinge", is_disc=True)) * 0.5
+                od.zero_grad(); loss_d.backward(); od.step()
+                for p in D.parameters():
+                    p.requires_grad_(False)
+                total = loss_g + MD.gan_loss(D(preds), True, loss_type="hinge", is_disc=False) * cfg["loss"]["adversarial_weight"]
+                og.zero_grad(); total.backward(); og.step()
+                for p in D.parameters():
+                    p.requires_grad_(True)
+        else:
+            G.eval()
+
+            def step():
+                with torch.no_grad():
+                    G(mf, mk)
+        kind = "reference"
+    else:
+        from oracle import p2i_oracle as O
+        from p2igan_b200 import build_discriminator, build_generator
+        torch.manual_seed(2024)
+        g_sd = {k: v.detach().clone() for k, v in build_generator(cfg).state_dict().items()}
+        if train:
+            d_sd = {k: v.detach().clone() for k, v in build_discriminator(cfg).state_dict().items()}
+            og, od, it = {}, {}, [0]
+
+            def step():
+                it[0] += 1
+                O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it[0], idw="ref")
+        else:
+            def step():
+                with torch.no_grad():
+                    O.generator_forward(g_sd, mf, mk, idw="ref")
+        kind = "port"
     for _ in range(warmup):
-        it += 1
-        O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it, idw="ref")
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        it += 1
-        O.gan_train_step(g_sd, d_sd, fr, mf, mk, og, od, it, idw="ref")
+        step()
     dt = time.perf_counter() - t0
-    return n_events * steps / dt, cores, dt / steps
+    return B * steps / dt, cores, dt / steps, kind
 
 
-WORKLOADS = {
-    "train": ("train events/s (G+D step, 16x128x128)",
-              "full GAN training step (generator + dual-branch patch discriminator, weighted-L1 + temporal-KL + hinge, "
-              "2x Adam) p2igan_gan_baseline.json, batch 16/GPU, synthetic events 16x128x128 (BASELINE configs[2])"),
-    "infer": ("infer events/s (generator forward, 16x128x128)",
-              "P2IGAN generator-only inference, batch 32 synthetic radar-input events 16x128x128 (BASELINE configs[1])"),
-}
+def cpu_baseline_record(name, B, steps, warmup):
+    v, cores, spp, kind = cpu_events_per_s(name, B, steps, warmup)
+    what = ("the unmodified reference modules (p2igan_bench.models / .modules from the reference checkout, torch CPU fp32, "
+            "stepped in scripts/train.py:240-326's order)") if kind == "reference" else \
+        ("oracle/p2i_oracle.py, the torch CPU fp32 restatement of the reference with reference-style cdist/topk IDW "
+         "(the reference checkout is not present on this box)")
+    return {"value": v, "unit": "events/s", "cores": cores, "kind": kind, "s_per_step": spp,
+            "sample": f"{B} events/step x {steps} timed steps (+{warmup} warm-up) of the same workload: {what}"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_events = 4
-    steps, warmup = max(1, min(args.steps, 6)), 1          # bounded sample: ~10-20 s of CPU work on the box's host cores
-    fn = cpu_train_events_per_s if args.workload == "train" else cpu_generator_events_per_s
-    v, cores, spp = fn(n_events, steps, warmup)
-    metric, wl = WORKLOADS[args.workload]
+    metric, wl, train, B, HW, n_obs, _ = WORKLOADS[args.workload]
+    B = args.batch or B
+    steps, warmup = max(1, min(args.steps, 3)), 1      # bounded: the whole run ends within a few minutes of host-core work
+    rec = cpu_baseline_record(args.workload, B, steps, warmup)
+    v = rec["value"]
     line = {"impl": "reference", "metric": metric, "value": v, "unit": "events/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spp * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "events_per_step": n_events, "gauge_pixels": N_OBS},
-            "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_events} events/step x {steps} steps of the same workload (oracle/p2i_oracle.py: "
-                                       "torch CPU fp32 restatement of the reference, reference-style cdist/topk IDW)"},
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": rec["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": n_obs,
+                       "note": "CPU arm: one process on the box's host cores regardless of --gpus"},
+            "cpu_baseline": rec,
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-# ----------------------------------------------------------------------------------------------- our arm
+# ----------------------------------------------------------------------------------------------- timers of the roofline pass
+def conv_desc_flops(desc):
+    """Algorithmic FLOPs (2*MAC of the reference's conv call, SURVEY.md 8d) of one p2i_conv_igemm / p2i_conv_wgrad launch from
+    its P2iConvDesc.  Space-to-depth k=2 layers execute 16/9 of the algorithmic taps, the channel-padded first 2-D layer
+    64/16 of the channels; a temporally TRANSPOSED stride-2 launch (data gradient of d3d.6) touches each of its T_in
+    gradient frames with kt taps, i.e. T_in*kt (frame, tap) pairs, not T_out*kt (VERDICT r1 weak #4)."""
+    smp, Tin, Tout, H_, W_, Cin, Cout, kt, k = [desc[i] for i in range(9)]
+    stride_t, t_transposed = desc[11], desc[12]
+    frames_taps = (Tin if (t_transposed and stride_t == 2) else Tout) * kt
+    f = 2.0 * smp * frames_taps * H_ * W_ * Cout * Cin * k * k
+    if k == 2:
+        f *= 9.0 / 16.0
+    if kt == 1 and k == 3 and Cin == 64 and Cout == 64:
+        f *= 16.0 / 64.0
+    return f
+
+
 class ConvTimer:
-    """CUDA events around every tensor-core conv launch (forward / dgrad: conv_igemm_kernel; wgrad: conv_wgrad_kernel)
-    with the ALGORITHMIC FLOPs of each launch (space-to-depth k=2 layers count 9/16 of the executed MACs, the
-    channel-padded first 2-D discriminator layer 16/64)."""
+    """CUDA events around every tensor-core conv launch (forward / dgrad: conv_halo_kernel; wgrad: conv_wgrad_kernel)
+    with the ALGORITHMIC FLOPs of each launch."""
 
     CONV_ENTRY = ("p2i_conv_igemm", "p2i_conv2d_igemm_fwd", "p2i_conv_wgrad", "p2i_conv2d_wgrad")
 
@@ -242,20 +327,11 @@ class ConvTimer:
             B_, H_, W_, Cin = x.shape
             return self._rec("wgrad", 2.0 * B_ * H_ * W_ * dy.shape[3] * Cin * ks * ks, o_wg, x, dy, ks, *a, **k)
 
-        def dfl(desc):
-            smp, Tin, Tout, H_, W_, Cin, Cout, kt, k = [desc[i] for i in range(9)]
-            f = 2.0 * smp * Tout * H_ * W_ * Cout * Cin * kt * k * k
-            if k == 2:
-                f *= 9.0 / 16.0
-            if kt == 1 and k == 3 and Cin == 64 and Cout == 64:
-                f *= 16.0 / 64.0
-            return f
-
         def dig(x, w, desc, *a, **k):
-            return self._rec("igemm", dfl(desc), d_ig, x, w, desc, *a, **k)
+            return self._rec("igemm", conv_desc_flops(desc), d_ig, x, w, desc, *a, **k)
 
         def dwg(x, dy, dW, desc):
-            return self._rec("wgrad", dfl(desc), d_wg, x, dy, dW, desc)
+            return self._rec("wgrad", conv_desc_flops(desc), d_wg, x, dy, dW, desc)
 
         ops.conv2d_cl, ops.conv2d_wgrad = cl, wg
         disc_ops.conv_igemm, disc_ops.conv_wgrad = dig, dwg
@@ -307,11 +383,347 @@ class ConvTimer:
         return out
 
 
+def _hbm_bytes_table(model_bytes):
+    """entry point -> algorithmic HBM bytes of ONE call as a function of its named integer arguments (a = dict of the C
+    arguments by name; pointers are None or ctypes objects).  bf16 activations: 2 B/element, model I/O fp32.  Table-driven
+    entry points (whole-model launches) take their per-call bytes from `model_bytes`."""
+    px = lambda a: a["B"] * a["H"] * a["W"]                                     # noqa: E731
+    return {
+        "p2i_points_extract": lambda a: 4 * a["B"] * a["T"] * a["H"] * a["W"],
+        "p2i_idw_knn_fwd": lambda a: 36 * a["B"] * a["T"] * a["H"] * a["W"],        # 4 idx + 4 w (32 B) read, 4 B written per query
+        "p2i_idw_knn_bwd": lambda a: 36 * a["B"] * a["T"] * a["H"] * a["W"],
+        "p2i_stem_fwd": lambda a: (64 + 128) * px(a),                                # 16 ch f32 in, 64 ch bf16 out
+        "p2i_stem_bwd": lambda a: (128 + 64 + 64) * px(a),
+        "p2i_pyramid_fwd": lambda a: (128 + 32 + 16) * px(a),
+        "p2i_pyramid_bwd": lambda a: (128 + 32 + 16 + 128) * px(a),
+        "p2i_upmod_fwd": lambda a: a["B"] * a["h"] * a["w"] * a["C"] * (2 + 8 + (8 if a["skip"] is not None else 0)),
+        "p2i_upmod_bwd": lambda a: a["B"] * a["h"] * a["w"] * a["C"] * (8 + 2 + 2),
+        "p2i_head_fwd": lambda a: (128 + 64) * px(a),
+        "p2i_head_bwd": lambda a: (64 + 64 + 128 + 128) * px(a),
+        "p2i_rec_loss_fwd": lambda a: 8 * a["B"] * a["T"] * a["HW"],
+        "p2i_rec_loss_bwd": lambda a: 12 * a["B"] * a["T"] * a["HW"],
+        "p2i_disc_pack_input": lambda a: (64 + 128) * px(a),
+        "p2i_disc_unpack_input_grad": lambda a: (128 + 64) * px(a),
+        "p2i_d3d_first_fwd": lambda a: (4 + 16) * a["B"] * a["T"] * a["H"] * a["W"],
+        "p2i_d3d_first_bwd": lambda a: (16 + 4 + (4 if a["dx"] is not None else 0)) * a["B"] * a["T"] * a["H"] * a["W"],
+        "p2i_d2d_last_fwd": lambda a: (2 * a["C"] + 4) * px(a),
+        "p2i_d2d_last_bwd": lambda a: (4 * a["C"] + 4) * px(a),
+        "p2i_colsum_bf16": lambda a: 2 * a["rows"] * a["C"],
+        "p2i_disc_tail_fwd": lambda a: 2 * a["B"] * a["T"] * a["h"] * a["w"] * a["C"],
+        "p2i_disc_tail_bwd": lambda a: 4 * a["B"] * a["T"] * a["h"] * a["w"] * a["C"],
+        "p2i_doconv_compose_fwd": lambda a: model_bytes["doconv_fwd"],
+        "p2i_doconv_compose_bwd": lambda a: model_bytes["doconv_bwd"],
+        "p2i_spectral_norm": lambda a: model_bytes["sn_fwd"],
+        "p2i_disc_pack_weights": lambda a: model_bytes["sn_pack"],
+        "p2i_spectral_norm_bwd": lambda a: model_bytes["sn_bwd"],
+        "p2i_adam_step": lambda a: model_bytes["adam"].get(a["n_chunks"], 28 * a["n_chunks"] * model_bytes["adam_chunk"]),
+    }
+
+
+class GlueTimer:
+    """CUDA events around EVERY call of a bandwidth-bound entry point of the library (everything except the tensor-core conv
+    entry points), with its algorithmic bytes -> achieved GB/s against the measured HBM bandwidth (row 'HBM-roofline
+    fractions' of VERDICT r1).  In-situ numbers: inputs a previous kernel just wrote may come from the 126 MB L2, so a
+    fraction above 1.0 is possible and says 'served from L2'; the brackets contain two timestamps and a dispatch, so small
+    kernels read low."""
+
+    def __init__(self, model_bytes):
+        self.table = _hbm_bytes_table(model_bytes)
+        self.rec = {}
+
+    def install(self):
+        from p2igan_b200._lib import LIB
+        lib_call = type(LIB).call
+        protos = LIB.protos
+
+        def call(name, *args):
+            fn = self.table.get(name)
+            if fn is None:
+                return lib_call(LIB, name, *args)
+            a = {an: v for (_, an), v in zip(protos[name][1], args)}
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = lib_call(LIB, name, *args)
+            e.record()
+            self.rec.setdefault(name, []).append((s, e, float(fn(a))))
+            return r
+        LIB.call = call
+
+    def remove(self):
+        from p2igan_b200._lib import LIB
+        if "call" in LIB.__dict__:
+            del LIB.call
+
+    def result(self, steps, hbm_gbs):
+        torch.cuda.synchronize()
+        out = []
+        for name, lst in self.rec.items():
+            ms = sum(s.elapsed_time(e) for s, e, _ in lst)
+            by = sum(b for _, _, b in lst)
+            gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else None
+            out.append({"entry": name, "launches_per_step": len(lst) // steps, "ms_per_step": ms / steps,
+                        "algorithmic_mb_per_step": by / steps / 1e6, "achieved_gbs": gbs,
+                        "frac_of_hbm": (gbs / hbm_gbs) if gbs else None})
+        out.sort(key=lambda r: -r["ms_per_step"])
+        return out
+
+
+def _model_bytes(G, D, ts):
+    """Algorithmic bytes per call of the whole-model (table-driven) launches."""
+    do_f = do_b = 0
+    for _, c in G._res_convs():
+        C = c.in_channels
+        do_f += 36 * C * C + 2 * 324 * C + 2 * 18 * C * C          # W, D, D_diag fp32 in; two bf16 operands out
+        do_b += 36 * C * C + 36 * C * C + 2 * 324 * C + 72 * C * C + 648 * C   # arena + W, D, D_diag in; dW, dD read-modify-write
+    mb = {"doconv_fwd": do_f, "doconv_bwd": do_b, "adam": {}, "adam_chunk": 0}
+    if D is not None:
+        nw = sum(p.numel() for n, p in D.named_parameters() if n.endswith("weight_orig"))
+        mb["sn_fwd"], mb["sn_pack"], mb["sn_bwd"] = 8 * nw, 8 * nw, 16 * nw   # W read twice | W in, two bf16 out | dW, W in, dW out (x2)
+    if ts is not None:
+        from p2igan_b200._lib import LIB
+        chunk = LIB.load().p2i_adam_chunk_elems()
+        mb["adam_chunk"] = chunk
+        for opt in (ts.opt_g, ts.opt_d):
+            if opt is None:
+                continue
+            sizes = [p.numel() for g in opt.param_groups for p in g["params"] if p.grad is not None]
+            n_chunks = sum((n + chunk - 1) // chunk for n in sizes)
+            mb["adam"][n_chunks] = 28 * sum(sizes)                   # p, g, m, v read; p, m, v written
+    return mb
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+class Workload:
+    """One BASELINE config on this rank's GPU: models, rotating synthetic batches, the graphed step and its e2e pipeline."""
+
+    def __init__(self, name, args, world, rank, dev, batch=None, use_graph=True):
+        from p2igan_b200 import build_discriminator, build_generator
+        from p2igan_b200.train_step import GANTrainStep, GraphedDPStep, GraphedStep
+        import torch.distributed as dist
+        self.name = name
+        self.metric, self.desc, self.train, B, HW, n_obs, self.cfg_index = WORKLOADS[name]
+        self.B = B = batch or B
+        self.HW, self.n_obs, self.world, self.rank, self.dev = HW, n_obs, world, rank, dev
+        cfg = synth.make_cfg(HW, HW)
+        torch.manual_seed(2024)
+        self.G = build_generator(cfg).to(dev)
+        self.D = build_discriminator(cfg).to(dev) if self.train else None
+        self.ts = None
+        self.exchange = "none"
+        if self.train:
+            self.G.train(); self.D.train()
+            # gradient exchange between ranks: "peer" = one NVLink peer-memory all-reduce kernel per model inside the step's
+            # single CUDA graph (p2igan_b200/peer.py); "nccl" = two NCCL all-reduces between three CUDA graphs
+            self.exchange = os.environ.get("P2I_DP_EXCHANGE", "peer") if world > 1 else "none"
+            self.ts = GANTrainStep(cfg, self.G, self.D, peer_exchange=(self.exchange == "peer"))
+            if world > 1 and self.exchange == "peer" and not self.ts.peer_exchange:
+                self.exchange = "nccl"            # CUDA IPC unavailable on this box: collective fallback (see GANTrainStep)
+        else:
+            self.G.eval()
+        # four rotating batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
+        self.batches = [make_inputs(name, B, HW, n_obs, 1000 * rank + i, dev) for i in range(4)]
+        self.host = [tuple(t.cpu().pin_memory() for t in b) for b in self.batches[:2]]
+        self.res_shape = (6,) if self.train else (B, T, 1, HW, HW)
+        self.res_host = torch.empty(self.res_shape, dtype=torch.float32).pin_memory()
+        LOSS_KEYS = ("rec", "pool", "reg", "adv", "dis", "total")
+        ts, G = self.ts, self.G
+
+        def eager(fr, mf, mk):
+            if self.train:
+                o = ts.step(fr, mf, mk)
+                return torch.stack([o[k] for k in LOSS_KEYS])
+            with torch.no_grad():
+                return G(mf, mk)
+        self.eager = eager
+        # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch.  Multi-GPU
+        # training with the NCCL exchange replays three graphs with the two all-reduces between them (GraphedDPStep).
+        self.graphed = None
+        if use_graph:
+            if world > 1 and self.train and self.exchange != "peer":
+                dp = GraphedDPStep(ts, self.batches[0], warmup=3)
+
+                class _DP:
+                    static_in = dp.static_in
+
+                    def __call__(self, *inp):
+                        o = dp(*inp)
+                        return torch.stack([o[k] for k in LOSS_KEYS])
+                self.graphed = _DP()
+            else:
+                self.graphed = GraphedStep(eager, self.batches[0], warmup=3)
+        self.run = self.graphed if self.graphed is not None else eager
+        self._dist = dist
+        self._e2e_ready = False
+
+    def barrier(self):
+        if self.world > 1:
+            self._dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(self, i):
+        return self.run(*self.batches[i % 4])
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, software-pipelined over three streams
+    # (H2D of step i+1 and D2H of step i-1 overlap the compute of step i; every copy is inside the timed region)
+    def _e2e_setup(self):
+        dev = self.dev
+        self.main = torch.cuda.current_stream()
+        self.s_h2d, self.s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.stage_in = [tuple(torch.empty_like(t) for t in self.batches[0]) for _ in range(2)]
+        self.stage_out = [torch.empty(self.res_shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        mk = lambda: [torch.cuda.Event() for _ in range(2)]       # noqa: E731
+        self.ev_in_ready, self.ev_in_free, self.ev_out_ready, self.ev_out_free = mk(), mk(), mk(), mk()
+        self._e2e_ready = True
+
+    def e2e_step(self, i):
+        k = i % 2
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_in_free[k])
+            for j in ((0, 1, 2) if self.train else (1, 2)):       # inference reads masked_frames and masks only
+                self.stage_in[k][j].copy_(self.host[k][j], non_blocking=True)
+            self.ev_in_ready[k].record(self.s_h2d)
+        self.main.wait_event(self.ev_in_ready[k])
+        o = self.run(*self.stage_in[k])                  # graphed: one D2D copy into the static inputs + replay
+        self.ev_in_free[k].record(self.main)
+        self.main.wait_event(self.ev_out_free[k])
+        self.stage_out[k].copy_(o.reshape(self.res_shape), non_blocking=True)
+        self.ev_out_ready[k].record(self.main)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_out_ready[k])
+            self.res_host.copy_(self.stage_out[k], non_blocking=True)
+            self.ev_out_free[k].record(self.s_d2h)
+
+    def e2e_drain(self):
+        self.main.wait_stream(self.s_d2h)
+        self.main.wait_stream(self.s_h2d)
+
+    def io_bytes(self):
+        px = self.B * T * self.HW * self.HW * 4
+        return (3 * px, 6 * 4) if self.train else (2 * px, px)
+
+    def time_steps(self, steps, warmup):
+        """(ms over exactly `steps` steps, wall t0, wall t1): CUDA events, barrier + synchronize on both sides."""
+        for i in range(max(3, warmup)):
+            self.step(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            self.step(i)
+        e1.record()
+        self.barrier()
+        return e0.elapsed_time(e1), t0, time.time()
+
+    def time_e2e(self, steps):
+        if not self._e2e_ready:
+            self._e2e_setup()
+        for i in range(2):
+            self.e2e_step(i)
+        self.e2e_drain()
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(steps):
+            self.e2e_step(i)
+        self.e2e_drain()
+        f1.record()
+        self.barrier()
+        return f0.elapsed_time(f1)
+
+    def captured_launches(self):
+        from p2igan_b200._lib import LIB
+        c0 = LIB.launch_count()
+        self.eager(*self.batches[0])
+        return LIB.launch_count() - c0
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def check_loss_finite(self):
+        """The timed steps really trained: the last step's losses are finite and the reconstruction loss is positive."""
+        if not self.train:
+            return None
+        v = self.step(0).detach().float().cpu().tolist()
+        ok = all(x == x and abs(x) < 1e30 for x in v) and v[0] > 0
+        return {"rec": v[0], "pool": v[1], "reg": v[2], "adv": v[3], "dis": v[4], "total": v[5], "finite": bool(ok)}
+
+
+def sub_record(name, args, world, rank, dev, steps):
+    """Compact record of another BASELINE config measured in the same run (value + e2e only)."""
+    w = Workload(name, args, world, rank, dev)
+    ms, _, _ = w.time_steps(steps, 3)
+    ms_e2e = w.time_e2e(steps)
+    h2d, d2h = w.io_bytes()
+    ev = w.B * world * steps
+    rec = {"metric": w.metric, "baseline_config": f"configs[{w.cfg_index}]", "workload": w.desc, "value": ev / (ms * 1e-3),
+           "unit": "events/s", "steps": steps, "ms_per_step": ms / steps, "events_per_step_per_gpu": w.B,
+           "e2e": {"value": ev / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "losses_last_step": w.check_loss_finite()}
+    if name == "stress256":
+        rec["metrics_sweep"] = metrics_sweep(dev)
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
+def metrics_sweep(dev, n_events=8, frames=20, HW=256, reps=10):
+    """RainfallMetricSuite.update on 8 events of 20x256x256 (configs[4]): events/s and the two kernels' achieved GB/s
+    (8 bytes read per pixel per pass: fused MAE/RMSE/contingency/FSS pass, SSIM pass)."""
+    from p2igan_b200 import MetricConfig, RainfallMetricSuite
+    from p2igan_b200._lib import LIB
+    _, _, hbm, _ = peaks()
+    g = torch.Generator().manual_seed(4)
+    sets = [((torch.rand(n_events, frames, 1, HW, HW, generator=g) ** 3 * 85.0).to(dev),
+             (torch.rand(n_events, frames, 1, HW, HW, generator=g) ** 3 * 85.0).to(dev)) for _ in range(3)]
+    suite = RainfallMetricSuite(MetricConfig()).to(dev)
+    lib_call = type(LIB).call
+    per = {"p2i_metrics_update": [], "p2i_ssim_update": []}
+
+    def call(name, *a):
+        if name in per:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = lib_call(LIB, name, *a)
+            e.record()
+            per[name].append((s, e))
+            return r
+        return lib_call(LIB, name, *a)
+    for p_, t_ in sets:
+        suite.update(p_, t_)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        suite.update(*sets[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    LIB.call = call
+    try:
+        for i in range(reps):
+            suite.update(*sets[i % 3])
+        torch.cuda.synchronize()
+    finally:
+        del LIB.call
+    by = 8.0 * n_events * frames * HW * HW
+    out = {"events_per_s": n_events / (ms * 1e-3), "ms_per_update": ms, "events_per_update": n_events,
+           "shape": [n_events, frames, 1, HW, HW], "l2": "3 rotating input sets of 84 MB each (the pair of one update exceeds what stays in L2)"}
+    for name, lst in per.items():
+        k_ms = sum(s.elapsed_time(e) for s, e in lst) / len(lst)
+        out[name] = {"ms": k_ms, "algorithmic_mb": by / 1e6, "achieved_gbs": by / (k_ms * 1e-3) / 1e9,
+                     "frac_of_hbm": by / (k_ms * 1e-3) / 1e9 / hbm}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from p2igan_b200 import build_discriminator, build_generator
+    from p2igan_b200 import set_stream_overlap
     from p2igan_b200._lib import LIB
-    from p2igan_b200.train_step import GANTrainStep, GraphedDPStep, GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -320,212 +732,119 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    train = args.workload == "train"
-    B = args.batch or (16 if train else 32)
-    cfg = synth.make_cfg(H, W)
+    w = Workload(args.workload, args, world, rank, dev, batch=args.batch or None, use_graph=not args.no_graph)
+    train, B = w.train, w.B
+    steps = args.steps
 
-    torch.manual_seed(2024)
-    G = build_generator(cfg).to(dev)
-    D = build_discriminator(cfg).to(dev) if train else None
-    if train:
-        G.train(); D.train()
-        # gradient exchange between ranks: "peer" = one NVLink peer-memory all-reduce kernel per model inside the step's
-        # single CUDA graph (p2igan_b200/peer.py); "nccl" = two NCCL all-reduces between three CUDA graphs
-        exchange = os.environ.get("P2I_DP_EXCHANGE", "peer") if world > 1 else "none"
-        ts = GANTrainStep(cfg, G, D, peer_exchange=(exchange == "peer"))
-        if world > 1 and exchange == "peer" and not ts.peer_exchange:
-            exchange = "nccl"            # CUDA IPC unavailable on this box: collective fallback (see GANTrainStep)
-    else:
-        G.eval()
-        exchange = "none"
-    # four rotating batches (per-rank seeds) so no step re-reads the previous step's inputs from L2
-    # frames differ per batch and rank; the gauge mask is ONE static 79-pixel pattern (seed 1), as the reference's 'stis'
-    # mask file is (data/sti_dataset.py:104-117, SURVEY.md 8d inputs 2-3)
-    mask = synth.make_mask(B, T, H, W, N_OBS, 1)
-    batches = []
-    for i in range(4):
-        fr = synth.make_batch(B, T, H, W, N_OBS, 1000 * rank + i)[0]
-        batches.append(tuple(t.to(dev) for t in (fr, fr * mask, mask)))
-    host = [tuple(t.cpu().pin_memory() for t in b) for b in batches[:2]]
-    out_host = torch.empty(B, T, 1, H, W, dtype=torch.float32).pin_memory()
-    loss_host = torch.empty(6, dtype=torch.float32).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def eager(fr, mf, mk):
-        if train:
-            o = ts.step(fr, mf, mk)
-            return torch.stack([o["rec"], o["pool"], o["reg"], o["adv"], o["dis"], o["total"]])
-        with torch.no_grad():
-            return G(mf, mk)
-
-    LOSS_KEYS = ("rec", "pool", "reg", "adv", "dis", "total")
-    # public API: the host-sync-free step captured once in a CUDA graph (GraphedStep), replayed per batch.  Multi-GPU
-    # training replays three graphs with the two NCCL all-reduces between them (GraphedDPStep).
-    graphed = None
-    if not args.no_graph:
-        if world > 1 and train and exchange != "peer":
-            dp = GraphedDPStep(ts, batches[0], warmup=3)
-
-            class _DP:
-                static_in = dp.static_in
-
-                def __call__(self, *inp):
-                    o = dp(*inp)
-                    return torch.stack([o[k] for k in LOSS_KEYS])
-            graphed = _DP()
-        else:
-            graphed = GraphedStep(eager, batches[0], warmup=3)
-    run = graphed if graphed is not None else eager
-
-    def step(i):
-        return run(*batches[i % 4])
-
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, software-pipelined over three streams
-    # (H2D of step i+1 and D2H of step i-1 overlap the compute of step i; every copy is inside the timed region)
-    main = torch.cuda.current_stream()
-    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    stage_in = [tuple(torch.empty_like(t) for t in batches[0]) for _ in range(2)]
-    res_shape = (6,) if train else (B, T, 1, H, W)
-    stage_out = [torch.empty(res_shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    ev_in_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_in_free = [torch.cuda.Event() for _ in range(2)]
-    ev_out_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_out_free = [torch.cuda.Event() for _ in range(2)]
-    res_host = loss_host if train else out_host
-
-    def e2e_step(i):
-        k = i % 2
-        with torch.cuda.stream(s_h2d):
-            s_h2d.wait_event(ev_in_free[k])
-            for j in ((0, 1, 2) if train else (1, 2)):       # inference reads masked_frames and masks only
-                stage_in[k][j].copy_(host[k][j], non_blocking=True)
-            ev_in_ready[k].record(s_h2d)
-        main.wait_event(ev_in_ready[k])
-        o = run(*stage_in[k])                       # graphed: one D2D copy into the static inputs + replay
-        ev_in_free[k].record(main)
-        main.wait_event(ev_out_free[k])
-        stage_out[k].copy_(o.reshape(res_shape), non_blocking=True)
-        ev_out_ready[k].record(main)
-        with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(ev_out_ready[k])
-            res_host.copy_(stage_out[k], non_blocking=True)
-            ev_out_free[k].record(s_d2h)
-
-    def e2e_drain():
-        main.wait_stream(s_d2h)
-        main.wait_stream(s_h2d)
-
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    l0 = LIB.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = LIB.launch_count() - l0
-    if graphed is not None:              # replays do not pass through the C entry points: count the captured launches
-        c0 = LIB.launch_count()
-        eager(*batches[0])
-        launches = (LIB.launch_count() - c0) * args.steps
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms, t_wall0, t_wall1 = w.time_steps(steps, args.warmup)
+    launches = w.captured_launches() * steps if w.graphed is not None else None
+    if launches is None:
+        l0 = LIB.launch_count()
+        w.step(0)
+        launches = (LIB.launch_count() - l0) * steps
+    clocks = sampler.window(t_wall0, t_wall1) if rank == 0 else None
+    ms_e2e = w.time_e2e(steps)
+    ms, ms_e2e = w.max_over_ranks(ms, ms_e2e)
 
-    for i in range(2):
-        e2e_step(i)
-    e2e_drain()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    e2e_drain()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    # ---- sustained leg: when K steps are shorter than 2 s, repeat the same step for >= 2 s (clock / power response)
+    sustained = None
+    if ms < 2000.0 and not args.no_extras:
+        n_s = int(2200.0 / (ms / steps)) + 1
+        ms_s, s0, s1 = w.time_steps(n_s, 0)
+        (ms_s,) = w.max_over_ranks(ms_s)
+        sustained = {"steps": n_s, "seconds": ms_s * 1e-3, "ms_per_step": ms_s / n_s, "value": B * world * n_s / (ms_s * 1e-3),
+                     "unit": "events/s", "clocks": sampler.window(s0, s1) if rank == 0 else None}
 
     # ---- dominant kernels: CUDA events around every tensor-core conv launch of the same steps (eager re-run so that
     # per-launch events can be recorded).  The side-stream overlap is switched OFF for this pass: a bracketed launch's
     # duration is then the kernel's own, not the kernel sharing its SMs with a concurrent glue kernel; the numbers of a
     # second pass with the overlap on (as in the timed step) are reported next to them.
-    from p2igan_b200 import set_stream_overlap
-    psteps = min(args.steps, 4)
+    psteps = min(steps, 4)
 
-    def timed_pass(group_runs):
-        """Eager steps with events around the conv launches (per run of consecutive launches or per launch).  Each step is enqueued behind a ~100 ms device-side sleep so
-        that the whole step sits in the launch queue before the GPU starts it: the events then bracket kernel time, not the
-        host's launch latency (an eager step is issued in ~7 ms, about as long as it runs)."""
-        t_ = ConvTimer(group_runs)
-        t_.install()
-        for i in range(psteps):
-            torch.cuda.synchronize()
-            torch.cuda._sleep(200_000_000)
-            eager(*batches[i % 4])
-        r_ = t_.result()
-        t_.remove()
-        return r_
+    def timed_pass(timer):
+        """Eager steps with events around the launches.  Each step is enqueued behind a ~100 ms device-side sleep so that the
+        whole step sits in the launch queue before the GPU starts it: the events then bracket kernel time, not the host's
+        launch latency (an eager step is issued in ~7 ms, about as long as it runs)."""
+        timer.install()
+        try:
+            for i in range(psteps):
+                torch.cuda.synchronize()
+                torch.cuda._sleep(200_000_000)
+                w.eager(*w.batches[i % 4])
+        finally:
+            timer.remove()
+        return timer
 
     set_stream_overlap(False)
-    kt = timed_pass(True)
+    kt = timed_pass(ConvTimer(True)).result()
+    hbm_kernels = None
+    if rank == 0 and not args.no_extras:
+        sustained_pk, burst_pk, hbm_pk, src_pk = peaks()
+        try:
+            hbm_kernels = timed_pass(GlueTimer(_model_bytes(w.G, w.D, w.ts))).result(psteps, hbm_pk)
+        except Exception as exc:               # diagnostics must never cost the headline number
+            hbm_kernels = {"error": repr(exc)}
     set_stream_overlap(True)
-    kt_ov = timed_pass(False)
+    kt_ov = timed_pass(ConvTimer(False)).result()
     ev_ms = ConvTimer.event_pair_overhead_ms()
+    losses = w.check_loss_finite()
 
-    if train and ts.peer_exchange:
-        ts.flat_g.peer.check()           # no exchange timed out
-        ts.flat_d.peer.check()
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    if train and w.ts.peer_exchange:
+        w.ts.flat_g.peer.check()           # no exchange timed out
+        w.ts.flat_d.peer.check()
+    sampler.stop()
     if rank == 0:
-        sustained, burst, hbm, src = peaks()
-        events = B * world * args.steps
-        metric, wl = WORKLOADS[args.workload]
+        sustained_pk, burst_pk, hbm_pk, src = peaks()
+        timed_s = ms * 1e-3
+        long_run = timed_s >= 2.0
+        peak = sustained_pk if long_run else burst_pk
+        peak_name = "bf16_tflops_sustained (timed region >= 2 s)" if long_run else \
+            "bf16_tflops (burst: the timed region and the roofline pass are far shorter than the seconds-long loop the sustained figure was measured in)"
+        events = B * world * steps
         ig_ms, ig_n, ig_fl, ig_br = kt["igemm"]
         wg_ms, wg_n, wg_fl, wg_br = kt["wgrad"]
         # no correction is applied: each bracket also contains the two timestamps and the kernel dispatch (ev_ms measures an
         # event pair around an empty kernel, reported for information), so `achieved` is a lower bound of the kernel's rate
         ig_tf = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else None
         wg_tf = wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None
-        if train:
-            h2d, d2h = 3 * B * T * H * W * 4, 6 * 4
-        else:
-            h2d, d2h = 2 * B * T * H * W * 4, B * T * H * W * 4
+        all_tf = (ig_fl + wg_fl) / ((ig_ms + wg_ms) * 1e-3) / 1e12 if (ig_ms + wg_ms) > 0 else None
+        h2d, d2h = w.io_bytes()
+        traffic, traffic_src = None, "not captured in this run (needs a profiler)"
+        tp = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+        if train and args.workload == "train" and os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj["mean_dram_bytes_per_launch"], tj["source"]
+            except Exception:
+                pass
         line = {
-            "metric": metric, "value": events / (ms * 1e-3), "unit": "events/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "metric": w.metric, "value": events / (ms * 1e-3), "unit": "events/s",
+            "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl, "events_per_step_per_gpu": B, "gauge_pixels": N_OBS, "gauge_mask": "one static pattern (stis), seed 1",
+            "config": {"workload": w.desc, "baseline_config": f"configs[{w.cfg_index}]", "events_per_step_per_gpu": B,
+                       "gauge_pixels": w.n_obs, "gauge_mask": "one static pattern (stis), seed 1",
                        "weights": "random init seed 2024",
-                       "launch": "eager" if graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train and exchange != "peer") else "CUDA graph replay"),
+                       "launch": "eager" if w.graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train and w.exchange != "peer") else "CUDA graph replay"),
                        "e2e_pipeline": "H2D / step / D2H on three streams, double-buffered",
                        "parallelism": ((f"data parallel over {world} GPU(s): flat D and G gradient buffers, " +
-                                        ("NVLink peer-memory all-reduce kernel (CUDA IPC) inside the step graph" if exchange == "peer"
-                                         else "NCCL all-reduce")) if train
+                                        ("NVLink peer-memory all-reduce kernel (CUDA IPC) inside the step graph" if w.exchange == "peer"
+                                         else ("NCCL all-reduce" if world > 1 else "no exchange at 1 GPU"))) if train
                                        else f"events sharded over {world} GPU(s), no collective"),
                        "l2": "no explicit flush: 4 rotating input batches and a per-step activation working set of several GB, "
                              "far above the 126 MB L2"},
             "e2e": {"value": events / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel / conv_igemm_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient launches)",
-                         "achieved": ig_tf, "peak": sustained, "unit": "TFLOP/s", "frac": (ig_tf / sustained) if ig_tf else None,
-                         "traffic": 17.6e6 if train else None, "traffic_source": "mean dram__bytes_read+write per launch over the 12 conv_halo launches of "
-                                                             "profiles/r1_conv_halo_ncu.txt (ncu --set full, train step, B=16)",
-                         "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+            "timed_region_s": timed_s,
+            "losses_last_step": losses,
+            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient launches)",
+                         "achieved": ig_tf, "peak": peak, "unit": "TFLOP/s", "frac": (ig_tf / peak) if ig_tf else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": f"{src} {peak_name}",
+                         "frac_of_sustained_peak": (ig_tf / sustained_pk) if ig_tf else None,
                          "kernel_ms_per_step": ig_ms / psteps, "launches_per_step": ig_n // psteps,
                          "event_pair_around_empty_kernel_us": ev_ms * 1e3,
                          "event_brackets_per_step": ig_br // psteps,
@@ -534,17 +853,33 @@ def run_ours(args):
                                      "side-stream overlap off (kernels alone), no overhead subtracted; per-launch brackets with the "
                                      f"overlap on, as in the timed step: {kt_ov['igemm'][0] / psteps:.3f} ms/step for the same launches",
                          "algorithmic_gflop_per_step": ig_fl / psteps / 1e9,
-                         "wgrad_kernel": {"achieved": wg_tf, "frac": (wg_tf / sustained) if wg_tf else None,
+                         "wgrad_kernel": {"achieved": wg_tf, "frac": (wg_tf / peak) if wg_tf else None,
                                           "kernel_ms_per_step": wg_ms / psteps, "launches_per_step": wg_n // psteps,
-                                          "algorithmic_gflop_per_step": wg_fl / psteps / 1e9}},
+                                          "algorithmic_gflop_per_step": wg_fl / psteps / 1e9},
+                         "all_tensor_kernels": {"achieved": all_tf, "frac": (all_tf / peak) if all_tf else None,
+                                                "kernel_ms_per_step": (ig_ms + wg_ms) / psteps,
+                                                "algorithmic_gflop_per_step": (ig_fl + wg_fl) / psteps / 1e9},
+                         "whole_step": {"achieved": (ig_fl + wg_fl) / psteps / (ms / steps * 1e-3) / 1e12,
+                                        "frac": (ig_fl + wg_fl) / psteps / (ms / steps * 1e-3) / 1e12 / peak,
+                                        "note": "tensor-core FLOPs of a step / wall time of a step (glue, losses, Adam included)"},
+                         "hbm_kernels": hbm_kernels, "hbm_peak_gbs": hbm_pk},
             "clocks": clocks,
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if world == 1 and not args.no_extras:
+            for name in ("infer", "gauge1pct", "stress256"):
+                if name == args.workload:
+                    continue
+                try:
+                    line[name] = sub_record(name, args, world, rank, dev, 20)
+                except Exception as exc:       # a sub-record must never cost the headline number
+                    line[name] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu:
-            fn = cpu_train_events_per_s if train else cpu_generator_events_per_s
-            v, cores, spp = fn(4, 5, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                                    "sample": "4 events/step x 5 timed steps (+1 warm-up) of the same workload (oracle/p2i_oracle.py, torch "
-                                              "CPU fp32 restatement of the reference, reference-style IDW)"}
+            try:
+                line["cpu_baseline"] = cpu_baseline_record(args.workload, B, 2, 1)
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -553,12 +888,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="train", choices=["train", "infer"])
-    ap.add_argument("--batch", type=int, default=0, help="events per step per GPU (default 16 train / 32 infer)")
+    ap.add_argument("--steps", type=int, default=400, help="timed steps (default: a >= 2 s timed region at 1 GPU)")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="events per step per GPU (default: the BASELINE config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained leg, the HBM kernel table and the other configs' sub-records")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -81,10 +81,11 @@ def idw_reference_style(points_xyz: Tensor, values: Tensor, shape: Tuple[int, in
                         tau: float = 0.05, chunk: int = 16384) -> Tensor:
     """IDW with the reference's own numerics: cdist (matmul path) + topk; tie order unspecified."""
     D, H, W = shape
-    gz, gy, gx = torch.meshgrid(torch.linspace(0, 1, D), torch.linspace(0, 1, H), torch.linspace(0, 1, W),
-                                indexing="ij")
+    dev = points_xyz.device          # CPU in the tests; tools/gpu_eager_reference.py runs the same code with CUDA tensors
+    gz, gy, gx = torch.meshgrid(torch.linspace(0, 1, D, device=dev), torch.linspace(0, 1, H, device=dev),
+                                torch.linspace(0, 1, W, device=dev), indexing="ij")
     grid = torch.stack([gx, gy, gz], dim=-1).reshape(-1, 3).contiguous()
-    out = torch.empty(grid.shape[0], dtype=torch.float32)
+    out = torch.empty(grid.shape[0], dtype=torch.float32, device=dev)
     for s in range(0, grid.shape[0], chunk):
         e = min(s + chunk, grid.shape[0])
         d = torch.cdist(grid[s:e], points_xyz)

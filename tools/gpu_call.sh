@@ -1,0 +1,31 @@
+#!/bin/bash
+# One gpurun call of round 2: GPU tests, bench lines, microbenchmarks, live graph timeline, ncu launch list + full capture.
+# usage: tools/gpu_call.sh <tag> [steps...]   (steps: tests bench umma eager graph ncu)
+tag=$1; shift
+steps="${@:-tests bench umma eager graph ncu}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+for s in $steps; do
+  case $s in
+    tests) timeout 1500 python -m pytest tests -m gpu -q -rf -p no:cacheprovider > gpurun_out/${tag}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.txt; tail -5 gpurun_out/${tag}_pytest.txt;;
+    smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.txt; tail -3 gpurun_out/${tag}_smoke.txt;;
+    bench) timeout 900 python bench.py > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "bench rc=$?"; head -c 600 gpurun_out/${tag}_bench_train.json;;
+    bench20) timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_train20.json 2> gpurun_out/${tag}_bench_train20.err; echo "bench20 rc=$?"; head -c 600 gpurun_out/${tag}_bench_train20.json;;
+    benchq) timeout 600 python bench.py --steps 50 --no-cpu --no-extras > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err; echo "benchq rc=$?"; head -c 400 gpurun_out/${tag}_bench_quick.json;;
+    infer) timeout 600 python bench.py --workload infer --steps 100 --no-extras > gpurun_out/${tag}_bench_infer.json 2> gpurun_out/${tag}_bench_infer.err; echo "infer rc=$?";;
+    ref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?";;
+    umma) timeout 120 tools/build/umma_rate > gpurun_out/${tag}_umma_rate.txt 2>&1; echo "umma rc=$?"; cat gpurun_out/${tag}_umma_rate.txt;;
+    eager) timeout 600 python tools/gpu_eager_reference.py > gpurun_out/${tag}_gpu_eager.json 2> gpurun_out/${tag}_gpu_eager.err; echo "eager rc=$?"; cat gpurun_out/${tag}_gpu_eager.json;;
+    graph) timeout 300 python tools/prof_graph.py gpurun_out/${tag}_graph_timeline.txt > gpurun_out/${tag}_graph_kernels.txt 2>&1; echo "graph rc=$?"; head -3 gpurun_out/${tag}_graph_kernels.txt;;
+    convab) timeout 600 python tools/bench_conv.py > gpurun_out/${tag}_conv_ab.txt 2>&1; echo "convab rc=$?";;
+    wgradab) timeout 600 python tools/bench_wgrad.py > gpurun_out/${tag}_wgrad_ab.txt 2>&1; echo "wgradab rc=$?";;
+    ncu)
+      timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err &&
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1600 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_list.log 2>&1
+      echo "ncu list rc=$?"
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_wgrad|conv_halo" -s 640 -c 165 -o gpurun_out/${tag}_conv_full \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_full.log 2>&1
+      echo "ncu full rc=$?";;
+  esac
+done

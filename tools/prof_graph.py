@@ -42,3 +42,9 @@ for e in ev:
     a[1] += e.time_range.end - e.time_range.start
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{v[1]:9.1f} us  n={v[0]:3d}  {k}")
+# full timeline (start relative to the first kernel, duration, stream): where the critical path and the overlaps are
+if len(sys.argv) > 1:
+    t0 = ev[0].time_range.start
+    with open(sys.argv[1], "w") as f:
+        for e in ev:
+            f.write(f"{(e.time_range.start - t0):10.2f} {(e.time_range.end - e.time_range.start):8.2f} s{getattr(e, 'device_resource_id', -1)} {e.name.split('(')[0][:70]}\n")
