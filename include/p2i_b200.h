@@ -37,6 +37,9 @@ long long p2i_launch_count(void);
  *   3000000 + nt*100 + stacked*10              : conv_wgrad_kernel        4000000 + mode : conv_wgrad2_kernel
  * The parity tests assert that the shapes they run select the instantiations the benchmark's train step launches. */
 int p2i_conv_last_variant(void);
+/* Programmatic dependent launch of the tensor-core conv kernels (prologue + weight fetch of a launch overlap the tail of
+ * its stream predecessor; CUDA-graph capturable).  Default on; 0 switches it off for A/B measurements. */
+int p2i_set_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * InputBlock  (p2igan_bench/modules/layer.py:307-361; gate :296-304; idw_3d_knn :259-293)
@@ -394,6 +397,13 @@ int p2i_peer_close(void* p);
 int p2i_peer_flags_bytes(void);
 int p2i_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, long long n, int* epoch_dev, int* err_dev,
                        void* stream);
+/* The same exchange restricted to elements [offset, offset + n) of the flat buffers (both multiples of 4) with `blocks`
+ * CTAs (0 = one per SM): the bucketed gradient exchange that runs on a side stream UNDER the backward pass -- a bucket is
+ * exchanged as soon as its gradients are final, with few enough CTAs to co-reside with the tensor-core kernels
+ * (what torch DDP's bucketed NCCL all-reduce would do).  Calls on one set of flags must be serialised
+ * (one stream) and issued in the same order on every rank. */
+int p2i_peer_allreduce_range(void* const* bufs, void* const* flags, int rank, int world, long long offset, long long n,
+                             int blocks, int* epoch_dev, int* err_dev, void* stream);
 
 /* Layout helpers for the per-layer drop-in modules: NCHW f32 <-> NHWC bf16. */
 int p2i_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, void* stream);

@@ -1,6 +1,7 @@
 // Error reporting, launch counter and the TMA descriptor encoder shared by all kernels.
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -12,6 +13,17 @@ std::atomic<long long> g_launches{0};
 static thread_local int g_last_variant = 0;
 void set_last_variant(int code) { g_last_variant = code; }
 int last_variant() { return g_last_variant; }
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("P2I_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v);
+    }
+    return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -85,4 +97,5 @@ int p2i_abi_version(void) { return 1; }
 const char* p2i_last_error(void) { return p2i::g_err; }
 long long p2i_launch_count(void) { return p2i::g_launches.load(); }
 int p2i_conv_last_variant(void) { return p2i::last_variant(); }
+int p2i_set_pdl(int on) { p2i::set_pdl(on); return P2I_OK; }
 }

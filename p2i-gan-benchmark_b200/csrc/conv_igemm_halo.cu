@@ -155,10 +155,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         if (elect_one()) {
-            // ------------------------------------------------------------ TMA producer: weights + activation boxes
+            // ------------------------------------------------------------ TMA producer: resident weights + activation boxes
             // CG == 2: completion bytes of BOTH CTAs land on the leader's barriers; only the leader posts expect_tx
             const int b_row0 = nt * NT + static_cast<int>(rank) * NB;
             if (RES) {
+                // weights were final two or more kernels ago (host contract): fetched BEFORE the dependency wait, under the
+                // predecessor's tail
                 const int nblk = p.KT * taps * cblocks;
                 if (rank == 0) mbar_expect_tx(bres, static_cast<uint32_t>(nblk) * BBLK * CG);
                 const uint32_t bar = (CG == 2) ? mapa_u32(smem_u32(bres), 0) : 0u;
@@ -169,8 +171,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         else tma_load_3d(dst, &tmB, bres, cb * 64, b_row0, t);
                     }
             }
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-            PROF_DECL(w_ea = 0, w_eb = 0, t_all = 0);
+            griddep_wait();                 // the activations (and everything else) come from the predecessor
+            griddep_launch_dependents();
+            uint32_t sa = 0, pa = 0;
+            PROF_DECL(w_ea = 0, t_all = 0);
             PROF_T0();
             for (int u = u0; u < p.units; u += ustep) {
                 const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
@@ -194,24 +198,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                             tc[i].y0 - p.pad, t_in, tc[i].smp);
                             if (++sa == static_cast<uint32_t>(p.SA)) { sa = 0; pa ^= 1; }
                         }
-                        if (!RES) {
-                            for (int t = 0; t < taps; ++t) {
-                                PROF_WAIT(w_eb, &emptyB[sb], pb ^ 1);
-                                if (rank == 0) mbar_expect_tx(&fullB[sb], BBLK * CG);
-                                if (CG == 2)
-                                    tma_load_3d_cg2(sB + sb * BBLK, &tmB, mapa_u32(smem_u32(&fullB[sb]), 0), cb * 64, b_row0,
-                                                    kt * taps + t);
-                                else
-                                    tma_load_3d(sB + sb * BBLK, &tmB, &fullB[sb], cb * 64, b_row0, kt * taps + t);
-                                if (++sb == static_cast<uint32_t>(p.SB)) { sb = 0; pb ^= 1; }
-                            }
+                    }
+                }
+            }
+#ifdef HALO_PROF
+            PROF_ADD(t_all);
+            if (blockIdx.x == 0) printf("halo prof A producer: total %lld  wait emptyA %lld\n", t_all, w_ea);
+#endif
+        }
+    } else if (warp == 3) {
+        if (!RES && elect_one()) {
+            // ------------------------------------------------------------ TMA producer: streamed weight blocks
+            // Same (unit, kt, cb, tap) order as the MMA issuer consumes them.  No dependency wait: the weights do not come from
+            // the predecessor, so the first SB blocks are in flight while the predecessor is still draining.
+            const int b_row0 = nt * NT + static_cast<int>(rank) * NB;
+            uint32_t sb = 0, pb = 0;
+            PROF_DECL(w_eb = 0, t_all = 0);
+            PROF_T0();
+            for (int u = u0; u < p.units; u += ustep) {
+                const int t_out0 = p.tmode ? halo_tile(p, tile_of(u, 0)).t_out : 0;
+                for (int kt = 0; kt < p.KT; ++kt) {
+                    bool skip;
+                    (void)halo_src_frame(p, t_out0, kt, skip);
+                    if (skip) continue;
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        for (int t = 0; t < taps; ++t) {
+                            PROF_WAIT(w_eb, &emptyB[sb], pb ^ 1);
+                            if (rank == 0) mbar_expect_tx(&fullB[sb], BBLK * CG);
+                            if (CG == 2)
+                                tma_load_3d_cg2(sB + sb * BBLK, &tmB, mapa_u32(smem_u32(&fullB[sb]), 0), cb * 64, b_row0,
+                                                kt * taps + t);
+                            else
+                                tma_load_3d(sB + sb * BBLK, &tmB, &fullB[sb], cb * 64, b_row0, kt * taps + t);
+                            if (++sb == static_cast<uint32_t>(p.SB)) { sb = 0; pb ^= 1; }
                         }
                     }
                 }
             }
 #ifdef HALO_PROF
             PROF_ADD(t_all);
-            if (blockIdx.x == 0) printf("halo prof producer: total %lld  wait emptyA %lld  wait emptyB %lld\n", t_all, w_ea, w_eb);
+            if (blockIdx.x == 0) printf("halo prof B producer: total %lld  wait emptyB %lld\n", t_all, w_eb);
 #endif
         }
     } else if (warp == 1) {
@@ -314,6 +340,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 2) {
         if (p.aux_mode != 0 && elect_one()) {
             // ------------------------------------------------------------ residual / mask tiles -> staging buffers
+            griddep_wait();
             uint32_t cs = 0;
             for (int u = u0; u < p.units; u += ustep) {
                 const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
@@ -335,6 +362,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int hh = (warp - 4) >> 2;
         const int row = ew * 32 + lane;
         const bool has_bias = p.bias != nullptr;
+        griddep_wait();          // nothing of this role touches global memory before the predecessor has completed
         if (has_bias)
             for (int i = threadIdx.x - 128; i < NT; i += HALO_EPI_THREADS) sBias[i] = __ldg(p.bias + nt * NT + i);
         named_bar_sync(1, HALO_EPI_THREADS);
@@ -513,13 +541,16 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.blockDim = dim3(HALO_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: the prologue and the weight fetch overlap the stream predecessor's tail (ptx.cuh)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<NT, RES, CG>, tmA, tmB, tmO, tmX, p);
     if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_halo launch: %s", cudaGetErrorString(e));
     P2I_CHECK_LAUNCH("conv_halo_kernel");

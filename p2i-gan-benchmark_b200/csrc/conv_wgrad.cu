@@ -79,6 +79,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     if (warp == 0) {
         if (elect_one()) {
+            griddep_wait();                 // both operands come from preceding kernels (ptx.cuh: programmatic dependent launch)
+            griddep_launch_dependents();
             uint32_t s = 0, ph = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int f = t / tiles_per_img, r = t - f * tiles_per_img;
@@ -124,6 +126,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp >= 4 && t_end > t_begin) {
         const int ew = warp - 4;
         const int row = ew * 32 + lane;
+        griddep_wait();
         mbar_wait(done, 0);
         tc_fence_after();
         for (int g = 0; g < ngroups; ++g) {
@@ -460,7 +463,20 @@ static int run_wgrad(const void* x, const void* dy, float* dW, const P2iConvDesc
         configured = true;
     }
     set_last_variant(3000000 + p.nt * 100 + (p.stacked ? 10 : 0));
-    conv_wgrad_kernel<<<items * ks, 256, WG_SMEM, as_stream(stream)>>>(tmX, tmY, p);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(items * ks);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = WG_SMEM;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tmX, tmY, p);
+        if (e != cudaSuccess) return fail(P2I_ERR_CUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
+    }
     P2I_CHECK_LAUNCH("conv_wgrad_kernel");
     return P2I_OK;
 }

@@ -28,7 +28,8 @@ struct PeerTable {
     int* flags[PEER_MAX_RANKS];      // flags[r]: rank r's flag array int[3][PEER_MAX_BLOCKS][PEER_MAX_RANKS]
     int* epoch;                      // local: incremented by peer_tick_kernel before every all-reduce
     int* err;                        // local: set to 1 when a spin timed out
-    long long n;                     // elements (multiple of 4)
+    long long n;                     // elements of the exchanged range (multiple of 4)
+    long long off4;                  // first float4 of the range inside the flat buffers (bucketed exchange)
     int rank, world;
 };
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
     peer_barrier(a, 0, epoch);
     {
         const long long s0 = static_cast<long long>(a.rank) * shard4;
-        float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]);
+        float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]) + a.off4;
         for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
             bool ok[U];
             long long j[U];
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
                 for (int r = 0; r < WT; ++r)
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        v[r][u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(a.buf[r]) + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[r][u] = ok[u] ? __ldcg(reinterpret_cast<const float4*>(a.buf[r]) + a.off4 + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     acc[u] = v[0][u];
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
 #pragma unroll
                 for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int r = 0; r < W; ++r) {
-                    const float4* src = reinterpret_cast<const float4*>(a.buf[r]);
+                    const float4* src = reinterpret_cast<const float4*>(a.buf[r]) + a.off4;
                     float4 v[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) v[u] = ok[u] ? __ldcg(src + j[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
     }
     peer_barrier(a, 1, epoch);
     {
-        float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]);
+        float4* dst = reinterpret_cast<float4*>(a.buf[a.rank]) + a.off4;
         if (WT) {
             // all W-1 owners' sub-ranges in flight together
             for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
 #pragma unroll
                 for (int k = 1; k < WT; ++k) {
                     const int s = (a.rank + k) % (WT ? WT : 1);
-                    const float4* src = reinterpret_cast<const float4*>(a.buf[s]);
+                    const float4* src = reinterpret_cast<const float4*>(a.buf[s]) + a.off4;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const long long j = static_cast<long long>(s) * shard4 + i + u * PEER_THREADS;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
             for (int k = 1; k < W; ++k) {
                 const int s = (a.rank + k) % W;                    // start with different owners on different ranks
                 const long long s0 = static_cast<long long>(s) * shard4;
-                const float4* src = reinterpret_cast<const float4*>(a.buf[s]);
+                const float4* src = reinterpret_cast<const float4*>(a.buf[s]) + a.off4;
                 for (long long i = lo + threadIdx.x; i < hi; i += U * PEER_THREADS) {
                     float4 v[U];
 #pragma unroll
@@ -210,19 +211,19 @@ extern "C" int p2i_peer_close(void* p) {
 
 extern "C" int p2i_peer_flags_bytes(void) { return 3 * PEER_MAX_BLOCKS * PEER_MAX_RANKS * static_cast<int>(sizeof(int)); }
 
-extern "C" int p2i_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, long long n, int* epoch_dev,
-                                  int* err_dev, void* stream) {
+static int peer_allreduce_launch(void* const* bufs, void* const* flags, int rank, int world, long long offset, long long n,
+                                 int blocks, int* epoch_dev, int* err_dev, void* stream) {
     P2I_CHECK_ARG(bufs && flags && epoch_dev && err_dev, "peer_allreduce: null pointer");
     P2I_CHECK_ARG(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "peer_allreduce: bad rank/world %d/%d", rank, world);
-    P2I_CHECK_ARG(n > 0 && n % 4 == 0, "peer_allreduce: n must be a positive multiple of 4");
+    P2I_CHECK_ARG(n > 0 && n % 4 == 0 && offset >= 0 && offset % 4 == 0, "peer_allreduce: offset and n must be multiples of 4 (n > 0)");
     PeerTable a;
     for (int r = 0; r < PEER_MAX_RANKS; ++r) {
         a.buf[r] = r < world ? static_cast<float*>(bufs[r]) : nullptr;
         a.flags[r] = r < world ? static_cast<int*>(flags[r]) : nullptr;
         P2I_CHECK_ARG(r >= world || (a.buf[r] && a.flags[r]), "peer_allreduce: null peer pointer for rank %d", r);
     }
-    a.epoch = epoch_dev; a.err = err_dev; a.n = n; a.rank = rank; a.world = world;
-    int grid = sm_count();
+    a.epoch = epoch_dev; a.err = err_dev; a.n = n; a.off4 = offset >> 2; a.rank = rank; a.world = world;
+    int grid = blocks > 0 ? blocks : sm_count();
     if (grid > PEER_MAX_BLOCKS) grid = PEER_MAX_BLOCKS;
     peer_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(epoch_dev);
     P2I_CHECK_LAUNCH("peer_tick_kernel");
@@ -232,4 +233,14 @@ extern "C" int p2i_peer_allreduce(void* const* bufs, void* const* flags, int ran
     else peer_allreduce_kernel<0><<<grid, PEER_THREADS, 0, as_stream(stream)>>>(a);
     P2I_CHECK_LAUNCH("peer_allreduce_kernel");
     return P2I_OK;
+}
+
+extern "C" int p2i_peer_allreduce(void* const* bufs, void* const* flags, int rank, int world, long long n, int* epoch_dev,
+                                  int* err_dev, void* stream) {
+    return peer_allreduce_launch(bufs, flags, rank, world, 0, n, 0, epoch_dev, err_dev, stream);
+}
+
+extern "C" int p2i_peer_allreduce_range(void* const* bufs, void* const* flags, int rank, int world, long long offset,
+                                        long long n, int blocks, int* epoch_dev, int* err_dev, void* stream) {
+    return peer_allreduce_launch(bufs, flags, rank, world, offset, n, blocks, epoch_dev, err_dev, stream);
 }

@@ -239,6 +239,16 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
                  : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream predecessor is
+// still running: everything before griddep_wait() (barrier init, TMEM allocation, loads of data that was final two or
+// more kernels ago) overlaps the predecessor's tail; griddep_wait() returns once the predecessor has completed and its
+// memory is visible.  griddep_launch_dependents() (issued AFTER the wait, so that at most two kernels of a chain are ever
+// in flight) lets the successor's CTAs be scheduled as soon as this kernel's CTAs free their SMs.  Both are no-ops for
+// a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

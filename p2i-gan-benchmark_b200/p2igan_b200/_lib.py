@@ -16,7 +16,8 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(os.path.dirname(PKG_DIR))
 HEADER = os.path.join(REPO_ROOT, "include", "p2i_b200.h")
-LIB_PATH = os.path.join(PKG_DIR, "libp2i_sm100a.so")
+# P2I_LIB_PATH: an alternative build of the same library (e.g. the -DHALO_PROF diagnostics build, tools/halo_prof.sh)
+LIB_PATH = os.environ.get("P2I_LIB_PATH") or os.path.join(PKG_DIR, "libp2i_sm100a.so")
 
 _CTYPE = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t}
 

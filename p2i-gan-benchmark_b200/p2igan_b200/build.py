@@ -11,14 +11,15 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(ROOT, "csrc")
 REPO = os.path.dirname(ROOT)
-OUT = os.path.join(PKG_DIR, "libp2i_sm100a.so")
-OBJ_DIR = os.path.join(ROOT, "build")
+PROF = bool(os.environ.get("P2I_HALO_PROF"))     # diagnostics build: separate objects and library, never the product .so
+OUT = os.path.join(PKG_DIR, "libp2i_sm100a_prof.so" if PROF else "libp2i_sm100a.so")
+OBJ_DIR = os.path.join(ROOT, "build_prof" if PROF else "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math"]
 # --use_fast_math would change division/sqrt rounding in the parity-sensitive kernels: keep IEEE there.
 NVCC_FLAGS.remove("--use_fast_math")
-if os.environ.get("P2I_HALO_PROF"):      # diagnostics build: the halo conv kernel prints per-role wait cycles
+if PROF:                                 # diagnostics build: the halo conv kernel prints per-role wait cycles
     NVCC_FLAGS.append("-DHALO_PROF")
 
 

@@ -150,7 +150,7 @@ class P2IGenerator(BaseNetwork):
         """copy.deepcopy / pickling of the module: drop transient kernel state (operand caches, gradient arena, CUDA stream)."""
         d = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
         d = dict(d)
-        for k in ("_wcache", "_gtable", "_side"):
+        for k in ("_wcache", "_gtable", "_side", "_bucket_hook"):
             d.pop(k, None)
         d["_wcache"] = None
         return d
@@ -248,6 +248,29 @@ class P2IGenerator(BaseNetwork):
             with torch.cuda.stream(wside):
                 ops.conv2d_wgrad(x, g, ks, out=out)
 
+        # The DO-Conv composition backward (arena -> dW, dD) runs per BUCKET of layers, on the stream of the weight gradients,
+        # as soon as the bucket's last weight gradient is launched; `_bucket_hook` (set by the data-parallel step) then
+        # exchanges that bucket's range of the flat gradient buffer while the backward pass continues.
+        convs = list(self._res_convs())
+        buckets = self._bwd_buckets()
+        hook = getattr(self, "_bucket_hook", None)
+
+        def finish_bucket(bi):
+            level, blocks = buckets[bi]
+            idx = [level * 2 * self.num_res + 2 * r + j for r in sorted(blocks) for j in (0, 1)]
+            names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for r in sorted(blocks) for j in (0, 1)]
+            key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
+            tabs = gt.setdefault("bwd_tables", {})
+            if bi not in tabs or tabs[bi][0] != key:
+                tab = pack_do_grad_table([(convs[i][1].W.data_ptr(), convs[i][1].D.data_ptr(), convs[i][1].D_diag.data_ptr(),
+                                           gviews[i].data_ptr(), tg[n + ".W"].data_ptr(), tg[n + ".D"].data_ptr(),
+                                           convs[i][1].in_channels) for i, n in zip(idx, names)])
+                tabs[bi] = (key, torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(dout.device))
+            with torch.cuda.stream(wside):
+                ops.doconv_compose_bwd(tabs[bi][1], len(idx), convs[idx[0]][1].in_channels)
+            if hook is not None:
+                hook([n + sfx for n in names for sfx in (".W", ".D")], wside)
+
         def eblock_bwd(level, d):
             base = level * 2 * self.num_res
             for r in reversed(range(self.num_res)):
@@ -256,6 +279,9 @@ class P2IGenerator(BaseNetwork):
                 dy = ops.conv2d_cl(d, bufs_t[base + 2 * r + 1], None, False, mask=y)
                 wgrad_side(a, dy, 3, gviews[base + 2 * r])
                 d = ops.conv2d_cl(dy, bufs_t[base + 2 * r], d, False)
+                for bi, (lv, blocks) in enumerate(buckets):
+                    if lv == level and min(blocks) == r:        # blocks are visited in descending order: r closes the bucket
+                        finish_bucket(bi)
             return d
 
         def up_bwd(i, d):
@@ -273,22 +299,6 @@ class P2IGenerator(BaseNetwork):
         d_x4 = d
         d = up_bwd(2, d)
         d_x8 = eblock_bwd(3, d)
-        # every weight gradient of the 32 DO-Conv layers is in the arena now: their composition backward (HBM-bound) runs on a
-        # side stream next to the stem / InputBlock backward chain (CUDA-core, latency-bound)
-        side = _overlap.pick(self._side_stream(dout.device), main, _overlap.G_DOCONV)
-        if side is not wside:            # the composition backward must see the complete arena; on the same stream it is ordered already
-            main.wait_stream(wside)
-        convs = list(self._res_convs())
-        names = [f"Decoder.{level}.layers.{r}.main.{j}.main.0" for level in range(4) for r in range(self.num_res) for j in range(2)]
-        key = tuple(tg[n + ".W"].data_ptr() for n in names) + tuple(tg[n + ".D"].data_ptr() for n in names)
-        if gt.get("bwd_key") != key:
-            tab = pack_do_grad_table([(c.W.data_ptr(), c.D.data_ptr(), c.D_diag.data_ptr(), g.data_ptr(), tg[n + ".W"].data_ptr(),
-                                       tg[n + ".D"].data_ptr(), c.in_channels) for (_, c), g, n in zip(convs, gviews, names)])
-            gt["bwd_table"] = torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(convs[0][1].W.device)
-            gt["bwd_key"] = key
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            ops.doconv_compose_bwd(gt["bwd_table"], len(convs), max(c.in_channels for _, c in convs))
         d_stem = ops.pyramid_bwd(sv["stem"], d_x4, d_x8)
         # (running the stem's weight gradient on the side stream as well was measured 2.7 % slower for the whole step: three
         # concurrent CUDA-core kernels contend for the same issue slots)
@@ -302,8 +312,18 @@ class P2IGenerator(BaseNetwork):
         w0, b0, w1, b1 = (p.detach().contiguous() for p in self.input.gate_params())
         ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals, tg["input.layers.0.conv.weight"],
                             tg["input.layers.0.conv.bias"], tg["input.layers.1.conv.weight"], tg["input.layers.1.conv.bias"])
-        main.wait_stream(side)
+        if wside is not main:
+            main.wait_stream(wside)
         return fresh
+
+    # (level, residual blocks) per gradient bucket, in the order the backward pass completes them.  The 512-channel level
+    # holds 74 % of the gradient bytes and arrives last: one bucket per residual block, so that its exchange keeps pace with
+    # the data-gradient chain instead of starting after it.
+    def _bwd_buckets(self):
+        n = self.num_res
+        if n != 4:
+            return [(lv, tuple(range(n))) for lv in range(4)]
+        return [(0, (0, 1, 2, 3)), (1, (0, 1, 2, 3)), (2, (2, 3)), (2, (0, 1)), (3, (3,)), (3, (2,)), (3, (1,)), (3, (0,))]
 
 
 class _GeneratorFn(torch.autograd.Function):

@@ -108,6 +108,12 @@ class PeerAllReduce:
         LIB.call("p2i_peer_allreduce", self._bufs, self._flags, self.rank, self.world, ctypes.c_longlong(self.n),
                  ctypes.c_void_p(self.state.data_ptr()), ctypes.c_void_p(self.state.data_ptr() + 4), stream())
 
+    def all_reduce_range(self, offset: int, n: int, blocks: int = 0) -> None:
+        """In-place sum of elements [offset, offset + n) only (multiples of 4), with ``blocks`` CTAs (0 = one per SM)."""
+        LIB.call("p2i_peer_allreduce_range", self._bufs, self._flags, self.rank, self.world, ctypes.c_longlong(int(offset)),
+                 ctypes.c_longlong(int(n)), int(blocks), ctypes.c_void_p(self.state.data_ptr()),
+                 ctypes.c_void_p(self.state.data_ptr() + 4), stream())
+
     def check(self) -> None:
         """Host-side check of the time-out word (synchronises; call outside the hot loop)."""
         if int(self.state[1]) != 0:

@@ -15,6 +15,7 @@ events; N ranks x b events  ==  one rank x N*b events up to fp32 summation order
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, Iterable, List
 
 import torch
@@ -41,12 +42,69 @@ class FlatGrads:
         else:
             self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
         o = 0
+        self.offsets = {}                     # id(param) -> (first element, numel) inside the flat buffer
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view(p.shape)
+            self.offsets[id(p)] = (o, p.numel())
             o += p.numel()
+        self.n = o
+        self._done = []                       # ranges already exchanged in this step (bucketed mode)
+        self._comm = None
 
     def zero(self):
         self.flat.zero_()
+
+    # ---- bucketed exchange (peer mode): ranges of the buffer are summed over the ranks on a side stream as soon as the
+    # backward pass has finalised them; finish() exchanges whatever is left and joins the side stream.
+    BUCKET_BLOCKS = int(os.environ.get("P2I_PEER_BLOCKS", "32"))     # CTAs of a bucket exchange: few enough to co-reside with GEMMs
+
+    def comm_stream(self) -> torch.cuda.Stream:
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.flat.device)
+        return self._comm
+
+    def exchange_params(self, params, producer: torch.cuda.Stream) -> bool:
+        """All-reduce(sum) the contiguous range spanned by `params` (final on stream `producer`) on the comm stream.
+        Returns False (nothing launched) when the range is not float4-aligned or not contiguous: finish() covers it."""
+        if self.peer is None or self.peer.world == 1:
+            return False
+        spans = sorted(self.offsets[id(p)] for p in params)
+        lo, hi = spans[0][0], spans[-1][0] + spans[-1][1]
+        if sum(n for _, n in spans) != hi - lo or lo % 4 or (hi - lo) % 4:
+            return False
+        comm = self.comm_stream()
+        comm.wait_stream(producer)
+        with torch.cuda.stream(comm):
+            self.peer.all_reduce_range(lo, hi - lo, self.BUCKET_BLOCKS)
+        self._done.append((lo, hi))
+        return True
+
+    def finish(self, group=None) -> float:
+        """Exchange every range no bucket covered, wait for the comm stream; returns the factor that turns the sums into means."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        world = dist.get_world_size(group)
+        if world == 1:
+            return 1.0
+        if self.peer is None or not self._done:
+            self._done = []
+            return self.all_reduce(group)
+        main = torch.cuda.current_stream()
+        comm = self.comm_stream()
+        comm.wait_stream(main)
+        done = sorted(self._done)
+        rest, pos = [], 0
+        n4 = (self.n + 3) // 4 * 4            # the peer buffer is padded to a multiple of 4 elements
+        for lo, hi in done + [(n4, n4)]:
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = max(pos, hi)
+        with torch.cuda.stream(comm):
+            for lo, hi in rest:
+                self.peer.all_reduce_range(lo, hi - lo, 0 if hi - lo > (1 << 20) else self.BUCKET_BLOCKS)
+        main.wait_stream(comm)
+        self._done = []
+        return 1.0 / world
 
     def all_reduce(self, group=None) -> float:
         """Sum over data-parallel ranks (one collective); returns the factor that turns the sum into a mean."""
@@ -93,6 +151,10 @@ class GANTrainStep:
         if not self.peer_exchange:
             self.flat_g = FlatGrads(generator.parameters())
             self.flat_d = FlatGrads(d_params) if self.use_gan else None
+        if self.peer_exchange and os.environ.get("P2I_BUCKETED", "1") != "0":
+            # bucketed, overlapped G exchange: the generator reports every finalised bucket of DO-Conv gradients (generator.py)
+            named = dict(generator.named_parameters())
+            generator._bucket_hook = lambda names, stream: self.flat_g.exchange_params([named[n] for n in names], stream)
         self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
         self.opt_d = None
         if self.use_gan:
@@ -154,7 +216,7 @@ class GANTrainStep:
         self.seg_a(frames, masked_frames, masks)
         d_scale = self.flat_d.all_reduce(self.pg) if self.use_gan else 1.0
         self.seg_b(d_scale)
-        g_scale = self.flat_g.all_reduce(self.pg)
+        g_scale = self.flat_g.finish(self.pg)        # buckets were exchanged under the backward pass; this covers the rest
         self.seg_c(g_scale)
         return self._out
 
