@@ -38,7 +38,7 @@ long long p2i_launch_count(void);
  * The parity tests assert that the shapes they run select the instantiations the benchmark's train step launches. */
 int p2i_conv_last_variant(void);
 /* Programmatic dependent launch of the tensor-core conv kernels (prologue + weight fetch of a launch overlap the tail of
- * its stream predecessor; CUDA-graph capturable).  Default on; 0 switches it off for A/B measurements. */
+ * its stream predecessor; CUDA-graph capturable).  Default off (measured neutral on the training step); 1 switches it on for A/B measurements. */
 int p2i_set_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------
@@ -354,6 +354,12 @@ typedef struct P2iAdamTensor {
  * read them.  grad_scale multiplies every gradient (1/world_size when the gradients hold a SUM over ranks). */
 int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The two halves of p2i_adam_step for a BUCKETED update (the parameters of a gradient bucket are updated as soon as the
+ * bucket is final, under the rest of the backward pass): p2i_adam_tick once per optimiser step (step += 1, bias corrections),
+ * then p2i_adam_apply per bucket with that bucket's tensor / chunk tables.  Every parameter must be applied exactly once. */
+int p2i_adam_tick(float* step_dev, float lr, float beta1, float beta2, void* stream);
+int p2i_adam_apply(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, const float* step_dev, float lr,
+                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 int p2i_adam_chunk_elems(void);
 
 /* SSIM of RegressionMetrics (metric.py:36,55-56,69 -> torchmetrics StructuralSimilarityIndexMeasure(data_range):

@@ -64,15 +64,28 @@ __global__ void __launch_bounds__(256) adam_kernel(const P2iAdamTensor* __restri
 
 }  // namespace p2i
 
-extern "C" int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
-                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
-    P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step_dev, "adam_step: bad arguments");
+extern "C" int p2i_adam_tick(float* step_dev, float lr, float beta1, float beta2, void* stream) {
+    P2I_CHECK_ARG(step_dev, "adam_tick: null pointer");
     p2i::adam_tick_kernel<<<1, 1, 0, p2i::as_stream(stream)>>>(step_dev, lr, beta1, beta2);
     P2I_CHECK_LAUNCH("adam_tick_kernel");
+    return P2I_OK;
+}
+
+extern "C" int p2i_adam_apply(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, const float* step_dev, float lr,
+                              float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step_dev, "adam_apply: bad arguments");
     p2i::adam_kernel<<<n_chunks, 256, 0, p2i::as_stream(stream)>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev), step_dev, lr,
                                                                    beta1, beta2, eps, grad_scale);
     P2I_CHECK_LAUNCH("adam_kernel");
     return P2I_OK;
+}
+
+extern "C" int p2i_adam_step(const P2iAdamTensor* tensors_dev, const int* chunks_dev, int n_chunks, float* step_dev, float lr,
+                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    P2I_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && step_dev, "adam_step: bad arguments");
+    int rc = p2i_adam_tick(step_dev, lr, beta1, beta2, stream);
+    if (rc) return rc;
+    return p2i_adam_apply(tensors_dev, chunks_dev, n_chunks, step_dev, lr, beta1, beta2, eps, grad_scale, stream);
 }
 
 extern "C" int p2i_adam_chunk_elems(void) { return p2i::ADAM_CHUNK; }

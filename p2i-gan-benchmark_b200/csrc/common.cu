@@ -17,8 +17,11 @@ static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
     int v = g_pdl.load(std::memory_order_relaxed);
     if (v < 0) {
+        // default OFF: measured neutral on the training step (6.44 vs 6.40 ms, profiles/r2_pdl_ab.txt) -- every kernel keeps
+        // one CTA per SM, so a dependent CTA only starts where its predecessor's CTA has already exited -- and an early-started
+        // kernel's waiting CTAs (220 KB of shared memory each) keep other streams' kernels off those SMs
         const char* e = getenv("P2I_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;
         g_pdl.store(v);
     }
     return v != 0;

@@ -44,7 +44,7 @@ int sm_count();
 // instantiation under test is the one the benchmark runs).
 void set_last_variant(int code);
 
-// Programmatic dependent launch of the tensor-core kernels (p2i_set_pdl; default on, P2I_PDL=0 in the environment turns it off).
+// Programmatic dependent launch of the tensor-core kernels (p2i_set_pdl; default off, P2I_PDL=1 in the environment turns it on).
 bool pdl_enabled();
 
 }  // namespace p2i

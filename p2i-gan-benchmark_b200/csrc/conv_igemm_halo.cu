@@ -25,6 +25,8 @@
 //       buffer ahead of time and overwritten in place.  Space-to-depth pack / unpack are just different store maps.
 // Warp roles (384 threads, persistent): warp0 TMA producer (A, B), warp1 MMA issuer (leader CTA of a pair only),
 // warp2 TMEM allocator + aux-tile producer, warps 4-11 epilogue (two warps per TMEM lane quarter, 32 columns each).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -40,6 +42,7 @@ struct HaloParams {
     int aux_mode;   // 0 none, 1 residual (added before the activation), 2 zero where aux <= 0, 3 x0.2 where aux <= 0
     int out_mode;   // 0 natural, 1 space-to-depth pack, 2 unpack
     int cq;         // out_mode 2: channels of the unpacked tensor (Cout / 4)
+    int dbg;        // -DHALO_PROF builds only (env P2I_HALO_DBG): 1 = the epilogue neither stages nor stores its tile, 2 = no TMEM reads either
     uint32_t offB, offS, offBias, offBar;
     const float* bias;
 };
@@ -146,7 +149,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ncta = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
     const int nt = cta % p.n_tiles;
     const int u0 = cta / p.n_tiles, ustep = ncta / p.n_tiles;
-    const int MBc = (CG == 2) ? 1 : p.MB;
+    // ONE: exactly one M tile per unit, known at compile time (pairs; resident-weight kernels never block over M).  Keeps the
+    // per-unit tile arrays of the role loops in registers: with a run-time count they live in local memory, and the LDL latency
+    // on the single MMA-issuing thread cost the 64-channel level 105 clk per instruction against a 64-clk floor (HALO_PROF).
+    constexpr bool ONE = (CG == 2) || RES;
+    const int MBc = ONE ? 1 : p.MB;
     // M tile i of unit u for this CTA, clamped: a pair's odd last unit computes a duplicate tile that is not stored
     auto tile_of = [&](int u, int i) -> int {
         const int mt = (CG == 2) ? (2 * u + static_cast<int>(rank)) : (u * p.MB + i);
@@ -177,7 +184,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             PROF_DECL(w_ea = 0, t_all = 0);
             PROF_T0();
             for (int u = u0; u < p.units; u += ustep) {
-                const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
+                const int nsub = ONE ? 1 : min(p.MB, p.m_tiles - u * p.MB);
                 TileCoord tc[2];
                 for (int i = 0; i < nsub; ++i) tc[i] = halo_tile(p, tile_of(u, i));
                 for (int kt = 0; kt < p.KT; ++kt) {
@@ -263,7 +270,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             PROF_DECL(w_fa = 0, w_fb = 0, w_te = 0, t_all = 0);
             PROF_T0();
             for (int u = u0; u < p.units; u += ustep) {
-                const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
+                const int nsub = ONE ? 1 : min(p.MB, p.m_tiles - u * p.MB);
                 const int t_out0 = tmode ? halo_tile(p, tile_of(u, 0)).t_out : 0;
                 PROF_WAIT(w_te, &tempty[acc], acc_par ^ 1);
                 tc_fence_after();
@@ -343,7 +350,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             griddep_wait();
             uint32_t cs = 0;
             for (int u = u0; u < p.units; u += ustep) {
-                const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
+                const int nsub = ONE ? 1 : min(p.MB, p.m_tiles - u * p.MB);
                 for (int i = 0; i < nsub; ++i) {
                     const TileCoord tc = halo_tile(p, tile_of(u, i));
                     for (int g = 0; g < NT / 64; ++g, ++cs) {
@@ -378,7 +385,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         PROF_DECL(w_tf = 0, w_st = 0, t_all = 0, t_store = 0, t_bar = 0);
         PROF_T0();
         for (int u = u0; u < p.units; u += ustep) {
-            const int nsub = (CG == 2) ? 1 : min(p.MB, p.m_tiles - u * p.MB);
+            const int nsub = ONE ? 1 : min(p.MB, p.m_tiles - u * p.MB);
             PROF_WAIT(w_tf, &tfull[acc], acc_par);
             tc_fence_after();
             for (int i = 0; i < nsub; ++i) {
@@ -393,8 +400,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t t_addr = tmem_base + acc * (MBc * NT) + i * NT + g * 64 + (static_cast<uint32_t>(ew * 32) << 16);
                     {
                         uint32_t v[32];
-                        tmem_ld32(t_addr + hh * 32, v);
-                        tmem_ld_wait();
+#ifdef HALO_PROF
+                        if (p.dbg & 2) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = 0u;
+                        } else
+#endif
+                        {
+                            tmem_ld32(t_addr + hh * 32, v);
+                            tmem_ld_wait();
+                        }
                         if (i == nsub - 1 && g == NT / 64 - 1) {   // accumulator fully read: release it to the MMA warp
                             tc_fence_before();
                             __syncwarp();
@@ -447,6 +462,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             o.y = pack_bf16x2(fv[2], fv[3]);
                             o.z = pack_bf16x2(fv[4], fv[5]);
                             o.w = pack_bf16x2(fv[6], fv[7]);
+#ifdef HALO_PROF
+                            if (!(p.dbg & 1))
+#endif
                             *sp = o;
                         }
                     }
@@ -462,6 +480,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (threadIdx.x == 128) {
                         const int n0 = nt * NT + g * 64;
                         const void* src = sS + b * HALO_STG;
+#ifdef HALO_PROF
+                        if (p.dbg & 1) {
+                        } else
+#endif
                         if (!store_ok) {
                             // duplicate tile of an odd last pair: nothing to write
                         } else if (p.out_mode == 0) {
@@ -494,7 +516,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             printf("halo prof epilogue: total %lld  wait tfull %lld  wait staging %lld  barrier %lld  store+wait_read %lld  chunks %u\n",
                    t_all, w_tf, w_st, t_bar, t_store, cs);
 #endif
-        if (threadIdx.x == 128) bulk_wait<0>();
+        // the staging tiles must outlive the TMA stores' READS only; kernel completion makes the writes visible
+        if (threadIdx.x == 128) bulk_wait_read<0>();
     }
 
     tc_fence_before();
@@ -579,6 +602,10 @@ int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const voi
     p.aux_mode = residual ? 1 : (mask ? (d.mask_mode == 2 ? 3 : 2) : 0);
     p.out_mode = d.out_mode;
     p.cq = d.Cout / 4;
+    p.dbg = 0;
+#ifdef HALO_PROF
+    if (const char* e = getenv("P2I_HALO_DBG")) p.dbg = atoi(e);
+#endif
     p.bias = bias;
 
     const int cblocks = d.Cin / 64;

@@ -403,7 +403,7 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
 // [l*R, (l+1)*R), R = Q/32 (half a frame at 16x128x128), and a block covers IDW_BWD_SPAN offsets of every run.  Lanes
 // then sit in different frames / far-apart rows and hit distinct points; each lane still streams through consecutive
 // addresses, so its 32-byte sectors are reused from L1 on the following iterations.
-constexpr int IDW_BWD_SPAN = 512;
+constexpr int IDW_BWD_SPAN = 64;       // offsets per block: 128 x B blocks at 16x128x128 (512 gave 16 x B blocks: latency-bound, 106-330 us)
 __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
                                                              const float* __restrict__ nbr_w, const int* __restrict__ counts,
                                                              const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {

@@ -115,6 +115,10 @@ class DiscState:
         # thin CUDA-core first layer then overlaps the 2-D branch's tensor-core kernels instead of queueing behind them
         self.side = torch.cuda.Stream(device=self.dev)
         self.aux = torch.cuda.Stream(device=self.dev)      # bias column-sums of the backward pass
+        # second lane for the paired fake / real calls of the D update (forward_pair_ctx, disc_bwd.backward_pair)
+        self.lane = torch.cuda.Stream(device=self.dev)
+        self.side2 = torch.cuda.Stream(device=self.dev)
+        self.aux2 = torch.cuda.Stream(device=self.dev)
 
     def next_set(self) -> _OperandSet:
         s = self.sets[self.calls % N_SETS]
@@ -131,38 +135,48 @@ def _state(D) -> DiscState:
     return st
 
 
-def forward_ctx(D, x: torch.Tensor, save: bool = False):
-    """x [B,T,1,H,W] f32 -> (logits [B,(H/4)(W/4)] f32, ctx).  Runs the spectral-norm hook semantics first:
-    in train() mode every call performs one power iteration and updates weight_u / weight_v in place."""
+def _check_input(D, x):
     require_cuda(x)
     B, T, C, H, W = x.shape
     if T * C != D.in_channels or T != 16:
         raise ValueError(f"P2IDiscriminator expects {D.in_channels} frames, got {T * C}")
     if H % 16 or W % 16:
         raise ValueError("P2IDiscriminator requires H and W to be multiples of 16")
-    state = _state(D)
+    return B, T, H, W
+
+
+def _prepare_operands(D, state) -> _OperandSet:
+    """The spectral-norm hook of ONE forward call on the current stream: in train() mode one power iteration that updates
+    weight_u / weight_v in place, sigma, and the packed bf16 GEMM operands W / sigma of the call's operand set."""
     st = state.next_set()
-    mods = state.mods
-    dev = x.device
-    xf = x.detach().reshape(B, T, H, W).contiguous().float()
     LIB.call("p2i_spectral_norm", ptr(st.sn_table), len(ALL_SN), st.max_rows, st.max_cols, 1 if D.training else 0, stream())
     LIB.call("p2i_disc_pack_weights", ptr(st.pack_table), len(TC_LAYERS), stream())
+    return st
+
+
+def _alloc_forward(B, T, H, W, dev):
+    """Every buffer of one forward call (allocate on the MAIN stream before any fork: the caching allocator is per stream)."""
     bf = torch.bfloat16
-    bias = {n: mods[n].bias.detach() for n in ALL_SN}
-    # every buffer is allocated on the main stream BEFORE the fork (the caching allocator is per stream)
-    a0 = torch.empty(B, H, W, 64, dtype=bf, device=dev)
-    y1 = torch.empty(B, H // 2, W // 2, 256, dtype=bf, device=dev)
-    y2 = torch.empty(B, H // 4, W // 4, 512, dtype=bf, device=dev)
-    y3 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
-    y4 = torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev)
-    o2d = torch.empty(B, H // 4, W // 4, dtype=torch.float32, device=dev)
     T2 = (T + 2 - 3) // 2 + 1
-    z1 = torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev)
-    z2 = torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev)
-    z3 = torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev)
-    z4 = torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev)
+    return dict(
+        a0=torch.empty(B, H, W, 64, dtype=bf, device=dev), y1=torch.empty(B, H // 2, W // 2, 256, dtype=bf, device=dev),
+        y2=torch.empty(B, H // 4, W // 4, 512, dtype=bf, device=dev), y3=torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev),
+        y4=torch.empty(B, H // 4, W // 4, 256, dtype=bf, device=dev), o2d=torch.empty(B, H // 4, W // 4, dtype=torch.float32, device=dev),
+        z1=torch.empty(B, T, H // 4, W // 4, 128, dtype=bf, device=dev), z2=torch.empty(B, T, H // 8, W // 8, 256, dtype=bf, device=dev),
+        z3=torch.empty(B, T, H // 8, W // 8, 128, dtype=bf, device=dev), z4=torch.empty(B, T2, H // 8, W // 8, 128, dtype=bf, device=dev),
+        m=torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev),
+        fused=torch.empty(B, (H // 4) * (W // 4), dtype=torch.float32, device=dev), T2=T2)
+
+
+def _forward_body(D, state, st, xf, bufs, side, save):
+    """The convolution stacks and the fused tail of one forward call on the CURRENT stream (2-D branch) and `side` (3-D branch)."""
+    B, T, H, W = xf.shape
+    mods = state.mods
+    bias = {n: mods[n].bias.detach() for n in ALL_SN}
+    a0, y1, y2, y3, y4, o2d = (bufs[k] for k in ("a0", "y1", "y2", "y3", "y4", "o2d"))
+    z1, z2, z3, z4, m, fused, T2 = (bufs[k] for k in ("z1", "z2", "z3", "z4", "m", "fused", "T2"))
     main = torch.cuda.current_stream()
-    side = _overlap.pick(state.side, main, _overlap.D_BRANCH)
+    side = _overlap.pick(side, main, _overlap.D_BRANCH)
     side.wait_stream(main)
     # ---- 3-D branch (side stream)
     with torch.cuda.stream(side):
@@ -171,7 +185,7 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
         conv_igemm(z1, st.w["d3d.2"], conv_desc(B, T, T, H // 4, W // 4, 128, 64, 3, 2, 1, 1, act=2, out_mode=1), bias=bias["d3d.2"], out=z2)
         conv_igemm(z2, st.w["d3d.4"], conv_desc(B, T, T, H // 8, W // 8, 256, 128, 3, 2, 1, 1, act=2), bias=bias["d3d.4"], out=z3)
         conv_igemm(z3, st.w["d3d.6"], conv_desc(B, T, T2, H // 8, W // 8, 128, 128, 3, 3, 1, 1, stride_t=2, act=2), bias=bias["d3d.6"], out=z4)
-    # ---- 2-D branch (main stream)
+    # ---- 2-D branch (current stream)
     LIB.call("p2i_disc_pack_input", ptr(xf), ptr(a0), B, 16, H, W, stream())
     conv_igemm(a0, st.w["d2d.0"], conv_desc(B, 1, 1, H, W, 64, 64, 1, 3, 1, 0, act=2, out_mode=1), bias=bias["d2d.0"], out=y1)
     conv_igemm(y1, st.w["d2d.2"], conv_desc(B, 1, 1, H // 2, W // 2, 256, 128, 1, 2, 1, 0, act=2, out_mode=1), bias=bias["d2d.2"], out=y2)
@@ -181,8 +195,6 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
              ptr(o2d), B, H // 4, W // 4, 256, stream())
     main.wait_stream(side)
     # ---- tail
-    m = torch.empty(B, H // 8, W // 8, dtype=torch.float32, device=dev)
-    fused = torch.empty(B, (H // 4) * (W // 4), dtype=torch.float32, device=dev)
     LIB.call("p2i_disc_tail_fwd", ptr(z4), ptr(mods["d3d.8"].weight_orig.detach()), ptr(st.sig("d3d.8")), ptr(bias["d3d.8"]),
              ptr(o2d), ptr(D.alpha2d.detach()), ptr(m), ptr(fused), B, T2, H // 8, W // 8, 128, H // 4, W // 4, stream())
     ctx = None
@@ -190,6 +202,47 @@ def forward_ctx(D, x: torch.Tensor, save: bool = False):
         ctx = dict(xf=xf, a0=a0, y1=y1, y2=y2, y3=y3, y4=y4, o2d=o2d, z1=z1, z2=z2, z3=z3, z4=z4, m=m, dims=(B, T, H, W, T2),
                    set=st)
     return fused, ctx
+
+
+def forward_ctx(D, x: torch.Tensor, save: bool = False):
+    """x [B,T,1,H,W] f32 -> (logits [B,(H/4)(W/4)] f32, ctx).  Runs the spectral-norm hook semantics first:
+    in train() mode every call performs one power iteration and updates weight_u / weight_v in place."""
+    B, T, H, W = _check_input(D, x)
+    state = _state(D)
+    xf = x.detach().reshape(B, T, H, W).contiguous().float()
+    st = _prepare_operands(D, state)
+    bufs = _alloc_forward(B, T, H, W, x.device)
+    return _forward_body(D, state, st, xf, bufs, state.side, save)
+
+
+def forward_pair_ctx(D, xa: torch.Tensor, xb: torch.Tensor, save: bool = False):
+    """D(xa) then D(xb) -- the two discriminator calls of the D update (scripts/train.py:264-265) -- with the reference's
+    semantics (two successive power iterations: call A uses sigma after the first, call B after the second) but with the two
+    convolution stacks on two stream lanes, so that one call's CUDA-core kernels (thin first 3-D layer, weight packing, tail)
+    run under the other call's tensor-core kernels.  -> ((logits_a, ctx_a), (logits_b, ctx_b))."""
+    Ba, T, H, W = _check_input(D, xa)
+    Bb, _, _, _ = _check_input(D, xb)
+    state = _state(D)
+    dev = xa.device
+    xfa = xa.detach().reshape(Ba, T, H, W).contiguous().float()
+    xfb = xb.detach().reshape(Bb, T, H, W).contiguous().float()
+    bufs_a, bufs_b = _alloc_forward(Ba, T, H, W, dev), _alloc_forward(Bb, T, H, W, dev)
+    main = torch.cuda.current_stream()
+    lane = _overlap.pick(state.lane, main, _overlap.D_PAIR)
+    st_a = _prepare_operands(D, state)
+    lane.wait_stream(main)
+    with torch.cuda.stream(lane):
+        out_a = _forward_body(D, state, st_a, xfa, bufs_a, state.side, save)
+    st_b = _prepare_operands(D, state)             # second power iteration: after the first (same stream), next to call A's convs
+    out_b = _forward_body(D, state, st_b, xfb, bufs_b, state.side2, save)
+    main.wait_stream(lane)
+    return out_a, out_b
+
+
+def discriminator_forward_pair(D, xa, xb):
+    """(D(xa), D(xb)) as one autograd node with the two calls on concurrent stream lanes (same values as two calls)."""
+    from .disc_bwd import DiscriminatorPairFn
+    return DiscriminatorPairFn.apply(D, xa, xb, *[p for _, p in D.named_parameters()])
 
 
 def discriminator_forward(D, x):

@@ -50,6 +50,12 @@ class P2IDiscriminator(BaseNetwork):
         from . import disc_ops
         return disc_ops.discriminator_forward(self, x)
 
+    def forward_pair(self, xa, xb):
+        """(self(xa), self(xb)) -- identical values and state updates (two successive power iterations in train mode) -- with
+        the two calls on concurrent stream lanes: the fake / real pair of the D update (scripts/train.py:264-265)."""
+        from . import disc_ops
+        return disc_ops.discriminator_forward_pair(self, xa, xb)
+
     def __getstate__(self):
         """copy.deepcopy / pickling of the module (EMA copies, torch.save(model)): drop the per-device kernel state (operand
         sets, device tables, CUDA streams); it is rebuilt on the next forward."""

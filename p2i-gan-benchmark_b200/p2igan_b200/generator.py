@@ -300,12 +300,18 @@ class P2IGenerator(BaseNetwork):
         d = up_bwd(2, d)
         d_x8 = eblock_bwd(3, d)
         d_stem = ops.pyramid_bwd(sv["stem"], d_x4, d_x8)
-        # (running the stem's weight gradient on the side stream as well was measured 2.7 % slower for the whole step: three
-        # concurrent CUDA-core kernels contend for the same issue slots)
-        dx_in, dw_stem = ops.stem_bwd(d_stem, sv["x_in"], wc["stem"])
+        # The stem's weight gradient (and its composition backward) only feed the gradient buffer: off the critical path, on
+        # the side stream behind the last weight gradients, next to the InputBlock backward chain.
         s = self.Convsin[0].main[0]
-        ops.doconv_compose_stem_bwd(s.W.detach(), s.D.detach(), s.D_diag.detach(), dw_stem, tg["Convsin.0.main.0.W"],
-                                    tg["Convsin.0.main.0.D"])
+        dw_stem = torch.zeros(64, 4, 9, dtype=torch.float32, device=dout.device)        # allocated on the main stream
+        sside = _overlap.pick(wside, main, _overlap.G_STEMDW)
+        dx_in = ops.stem_bwd_dx(d_stem, sv["x_in"], wc["stem"])
+        sside.wait_stream(main)
+        with torch.cuda.stream(sside):
+            ops.stem_bwd_dw(d_stem, sv["x_in"], wc["stem"], dw_stem)
+            ops.doconv_compose_stem_bwd(s.W.detach(), s.D.detach(), s.D_diag.detach(), dw_stem, tg["Convsin.0.main.0.W"],
+                                        tg["Convsin.0.main.0.D"])
+        keep.extend((d_stem, dw_stem))
         # InputBlock
         inp, pts, counts, src, table = sv["ictx"]
         dvals = ops.idw_knn_bwd(dx_in, table, counts, src, pts.shape[1])

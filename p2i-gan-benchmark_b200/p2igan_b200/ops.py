@@ -244,6 +244,22 @@ def stem_bwd(dy: Tensor, x: Tensor, w: Tensor):
     return dx, dw
 
 
+def stem_bwd_dx(dy: Tensor, x: Tensor, w: Tensor) -> Tensor:
+    """Input gradient of the stem only (the weight gradient is an independent kernel: stem_bwd_dw)."""
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    LIB.call("p2i_stem_bwd", ptr(_chk(dy, torch.bfloat16, "dy")), ptr(x), ptr(w), ptr(dx), None, B, H, W, stream())
+    return dx
+
+
+def stem_bwd_dw(dy: Tensor, x: Tensor, w: Tensor, dw: Tensor) -> Tensor:
+    """Weight gradient of the stem, accumulated into the zero-filled dw f32 [64,4,9]."""
+    B, C, H, W = x.shape
+    LIB.call("p2i_stem_bwd", ptr(_chk(dy, torch.bfloat16, "dy")), ptr(x), ptr(w), None, ptr(_chk(dw, torch.float32, "dw")), B, H, W,
+             stream())
+    return dw
+
+
 def doconv_compose_bwd(table_dev: Tensor, n_layers: int, max_channels: int) -> None:
     LIB.call("p2i_doconv_compose_bwd", ptr(table_dev), n_layers, max_channels, stream())
 

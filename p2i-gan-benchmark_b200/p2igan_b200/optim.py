@@ -90,6 +90,32 @@ class FusedAdam(torch.optim.Optimizer):
             self._tables[gi] = tb
         return tb
 
+    # ---- bucketed update: begin_step() once, then apply(params) per gradient bucket (each parameter exactly once per step)
+    @torch.no_grad()
+    def begin_step(self) -> None:
+        """step += 1 and the bias corrections of this optimiser step, on the current stream (before any apply())."""
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group["params"] if p.grad is not None]
+            if not plist:
+                continue
+            self._init_state(gi, group)
+            LIB.call("p2i_adam_tick", ptr(self.state[plist[0]]["step"]), float(group["lr"]), float(group["betas"][0]),
+                     float(group["betas"][1]), stream())
+
+    @torch.no_grad()
+    def apply(self, params, grad_scale: float = 1.0) -> None:
+        """Adam update of `params` (a subset of param group 0 with gradients) on the current stream, using the step counter
+        begin_step() advanced.  The work table of every distinct subset is built once and cached."""
+        group = self.param_groups[0]
+        plist = [p for p in params if p.grad is not None]
+        if not plist:
+            return
+        key = ("sub",) + tuple(id(p) for p in plist)
+        _, tens, chunks, n = self._table(key, plist)
+        LIB.call("p2i_adam_apply", ptr(tens), ptr(chunks), n, ptr(self.state[plist[0]]["step"]), float(group["lr"]),
+                 float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]), float(grad_scale), stream())
+        torch.autograd.graph.increment_version(plist)
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = closure() if closure is not None else None

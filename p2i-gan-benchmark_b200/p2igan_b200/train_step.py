@@ -151,11 +151,17 @@ class GANTrainStep:
         if not self.peer_exchange:
             self.flat_g = FlatGrads(generator.parameters())
             self.flat_d = FlatGrads(d_params) if self.use_gan else None
-        if self.peer_exchange and os.environ.get("P2I_BUCKETED", "1") != "0":
-            # bucketed, overlapped G exchange: the generator reports every finalised bucket of DO-Conv gradients (generator.py)
-            named = dict(generator.named_parameters())
-            generator._bucket_hook = lambda names, stream: self.flat_g.exchange_params([named[n] for n in names], stream)
         self.opt_g = FusedAdam(self.flat_g.params, lr=oc["lr"], betas=betas)
+        # Bucketed generator update: the generator reports every finalised bucket of DO-Conv gradients (generator.py); the
+        # bucket is exchanged over NVLink right away (peer mode) and its Adam update follows on the same side stream, under
+        # the rest of the backward pass.  Not with the NCCL exchange (the gradients are only summed after the backward pass).
+        world = dist.get_world_size(process_group) if multi else 1
+        self._g_scale = 1.0 / world
+        self._bucketed = (not multi or self.peer_exchange) and os.environ.get("P2I_BUCKETED", "1") != "0"
+        self._adam_done = set()
+        if self._bucketed:
+            self._g_named = dict(generator.named_parameters())
+            generator._bucket_hook = self._on_bucket
         self.opt_d = None
         if self.use_gan:
             # the optimiser sees ALL discriminator parameters in registration order, alpha3d included (grad None: skipped by
@@ -164,6 +170,17 @@ class GANTrainStep:
             self.opt_d = FusedAdam(list(discriminator.parameters()), lr=oc["lr"], betas=betas)
             from . import disc_bwd
             disc_bwd.prepare(discriminator)
+
+    def _on_bucket(self, names, producer: torch.cuda.Stream) -> None:
+        params = [self._g_named[n] for n in names]
+        run_on = producer
+        if self.peer_exchange:
+            if not self.flat_g.exchange_params(params, producer):
+                return                                   # left to FlatGrads.finish() and the closing Adam launch
+            run_on = self.flat_g.comm_stream()
+        with torch.cuda.stream(run_on):
+            self.opt_g.apply(params, grad_scale=self._g_scale)
+        self._adam_done.update(id(p) for p in params)
 
     def _gan(self, logits, real, is_disc):
         return gan_loss(logits, real, loss_type=self.gan_type, is_disc=is_disc, target_real_label=self.real_label,
@@ -183,8 +200,11 @@ class GANTrainStep:
         if self.use_gan:
             for p in D.parameters():
                 p.requires_grad_(True)
-            logits_fake = D(preds.detach())
-            logits_real = D(frames)
+            if hasattr(D, "forward_pair") and os.environ.get("P2I_D_PAIR", "1") != "0":
+                logits_fake, logits_real = D.forward_pair(preds.detach(), frames)      # two calls, two stream lanes
+            else:
+                logits_fake = D(preds.detach())
+                logits_real = D(frames)
             loss_d = (self._gan(logits_real, True, True) + self._gan(logits_fake, False, True)) * 0.5
             self.flat_d.zero()
             loss_d.backward()
@@ -201,12 +221,20 @@ class GANTrainStep:
             loss_g = loss_g + adv
             self._out["adv"] = adv.detach()
         self.flat_g.zero()
+        if self._bucketed:
+            self._adam_done.clear()
+            self.opt_g.begin_step()                      # before the backward pass forks its side streams
         loss_g.backward()
         self._out["total"] = loss_g.detach()
         self._preds = self._loss_g = None
 
     def seg_c(self, g_scale: float = 1.0) -> None:
-        self.opt_g.step(grad_scale=g_scale)
+        if self._bucketed:
+            rest = [p for p in self.flat_g.params if id(p) not in self._adam_done]
+            self.opt_g.apply(rest, grad_scale=g_scale)   # whatever no bucket covered (and everything, if no bucket fired)
+            self._adam_done.clear()
+        else:
+            self.opt_g.step(grad_scale=g_scale)
         if self.use_gan:
             for p in self.D.parameters():
                 p.requires_grad_(True)

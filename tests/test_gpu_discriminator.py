@@ -122,3 +122,38 @@ def test_discriminator_frozen_params_input_grad_only():
     x_ref = frames.clone().requires_grad_(True)
     (-O.discriminator_forward(dict(sd), x_ref, training=True).mean()).backward()
     assert rel_l2(x.grad, x_ref.grad) < 8e-2
+
+
+def test_forward_pair_equals_two_calls():
+    """D.forward_pair(fake, real) -- the D update's two calls on two stream lanes -- must give the values, the state updates
+    (two successive power iterations) and the gradients of D(fake) followed by D(real)."""
+    import copy
+    from p2igan_b200.losses import gan_loss
+    D1, _ = _pair(64, 64)
+    D2 = copy.deepcopy(D1)
+    frames, _, _ = synth.make_batch(2, 16, 64, 64, 12, 3)
+    fake = (frames.flip(1) * 0.7).to(DEV)
+    real = frames.to(DEV)
+    D1.train(); D2.train()
+
+    def loss_of(lf, lr_):
+        return 0.5 * (gan_loss(lr_, True, loss_type="hinge", is_disc=True) + gan_loss(lf, False, loss_type="hinge", is_disc=True))
+
+    fa = fake.clone().requires_grad_(True)
+    lf1, lr1 = D1(fa), D1(real)
+    loss_of(lf1, lr1).backward()
+    fb = fake.clone().requires_grad_(True)
+    lf2, lr2 = D2.forward_pair(fb, real)
+    loss_of(lf2, lr2).backward()
+    torch.cuda.synchronize()
+    assert torch.equal(lf1, lf2) and torch.equal(lr1, lr2)            # same kernels on the same operands
+    sd1, sd2 = D1.state_dict(), D2.state_dict()
+    for k in sd1:
+        if k.endswith("weight_u") or k.endswith("weight_v"):
+            assert torch.equal(sd1[k], sd2[k]), k
+    assert rel_l2(fb.grad, fa.grad) < 1e-5
+    for (n, p1), (_, p2) in zip(D1.named_parameters(), D2.named_parameters()):
+        if n == "alpha3d":
+            assert p2.grad is None
+            continue
+        assert rel_l2(p2.grad, p1.grad) < 1e-4, n                     # fp32 atomics: summation order only

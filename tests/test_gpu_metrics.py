@@ -137,7 +137,9 @@ def test_arbitrary_thresholds_and_scales_and_the_three_metric_classes():
     parts = {}
     for m in (reg, cat, fss):
         parts.update(m.compute())
-    assert parts == got
+    assert list(parts) == list(got)
+    for k in got:                                   # separate instances: the double-precision atomics sum in a different order
+        assert abs(parts[k] - got[k]) <= 1e-6 * max(1.0, abs(got[k])), (k, parts[k], got[k])
     fss.reset()
     assert fss.compute() == {}                          # counts == 0 -> key omitted (metric.py:178-179)
 

@@ -11,6 +11,12 @@ for s in $steps; do
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.txt; tail -3 gpurun_out/${tag}_smoke.txt;;
     bench) timeout 900 python bench.py > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "bench rc=$?"; head -c 600 gpurun_out/${tag}_bench_train.json;;
     bench20) timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_train20.json 2> gpurun_out/${tag}_bench_train20.err; echo "bench20 rc=$?"; head -c 600 gpurun_out/${tag}_bench_train20.json;;
+    prof) P2I_LIB_PATH=$PWD/p2i-gan-benchmark_b200/p2igan_b200/libp2i_sm100a_prof.so timeout 300 python tools/halo_prof.py > gpurun_out/${tag}_halo_prof.txt 2>&1; echo "prof rc=$?"; tail -4 gpurun_out/${tag}_halo_prof.txt;;
+    profdbg) for d in 1 3; do P2I_HALO_DBG=$d P2I_LIB_PATH=$PWD/p2i-gan-benchmark_b200/p2igan_b200/libp2i_sm100a_prof.so timeout 300 python tools/halo_prof.py 0 1 > gpurun_out/${tag}_halo_prof_dbg$d.txt 2>&1; echo "profdbg$d rc=$?"; done;;
+    pdl0) P2I_PDL=0 timeout 600 python bench.py --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_pdl0.json 2> gpurun_out/${tag}_bench_pdl0.err; echo "pdl0 rc=$?"; head -c 300 gpurun_out/${tag}_bench_pdl0.json;;
+    pdl1) P2I_PDL=1 timeout 600 python bench.py --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_pdl1.json 2> gpurun_out/${tag}_bench_pdl1.err; echo "pdl1 rc=$?"; head -c 300 gpurun_out/${tag}_bench_pdl1.json;;
+    testsel) timeout 900 python -m pytest tests -m gpu -q -rf -p no:cacheprovider -k "$P2I_TESTSEL" > gpurun_out/${tag}_pytest_sel.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_sel.txt; tail -30 gpurun_out/${tag}_pytest_sel.txt;;
+    peer2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_peer_allreduce.py > gpurun_out/${tag}_peer2.txt 2>&1; echo "peer2 rc=$?"; tail -15 gpurun_out/${tag}_peer2.txt;;
     benchq) timeout 600 python bench.py --steps 50 --no-cpu --no-extras > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err; echo "benchq rc=$?"; head -c 400 gpurun_out/${tag}_bench_quick.json;;
     infer) timeout 600 python bench.py --workload infer --steps 100 --no-extras > gpurun_out/${tag}_bench_infer.json 2> gpurun_out/${tag}_bench_infer.err; echo "infer rc=$?";;
     ref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?";;
@@ -24,7 +30,7 @@ for s in $steps; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1600 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
           python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_list.log 2>&1
       echo "ncu list rc=$?"
-      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_wgrad|conv_halo" -s 640 -c 165 -o gpurun_out/${tag}_conv_full \
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_wgrad|conv_halo" -s 640 -c ${P2I_NCU_COUNT:-24} -o gpurun_out/${tag}_conv_full \
           python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_full.log 2>&1
       echo "ncu full rc=$?";;
   esac

@@ -15,7 +15,11 @@ from p2igan_b200 import ops
 dev = "cuda:0"
 B = 16
 g = torch.Generator(device=dev).manual_seed(1)
+levels = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]
+print("P2I_HALO_DBG =", os.environ.get("P2I_HALO_DBG", "0"), flush=True)
 for lvl, C in enumerate((64, 128, 256, 512)):
+    if lvl not in levels:
+        continue
     hw = 128 >> lvl
     x = torch.randn(B, hw, hw, C, device=dev, generator=g).to(torch.bfloat16)
     r = torch.randn(B, hw, hw, C, device=dev, generator=g).to(torch.bfloat16)
