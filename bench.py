@@ -412,10 +412,12 @@ def _hbm_bytes_table(model_bytes):
         "p2i_disc_tail_fwd": lambda a: 2 * a["B"] * a["T"] * a["h"] * a["w"] * a["C"],
         "p2i_disc_tail_bwd": lambda a: 4 * a["B"] * a["T"] * a["h"] * a["w"] * a["C"],
         "p2i_doconv_compose_fwd": lambda a: model_bytes["doconv_fwd"],
-        "p2i_doconv_compose_bwd": lambda a: model_bytes["doconv_bwd"],
+        # per bucket: arena + W (fp32) + D, D_diag in, dW and dD read-modify-write; all layers of a bucket have max_channels channels
+        "p2i_doconv_compose_bwd": lambda a: a["n_layers"] * (144 * a["max_channels"] ** 2 + 1296 * a["max_channels"]),
         "p2i_spectral_norm": lambda a: model_bytes["sn_fwd"],
         "p2i_disc_pack_weights": lambda a: model_bytes["sn_pack"],
         "p2i_spectral_norm_bwd": lambda a: model_bytes["sn_bwd"],
+        "p2i_adam_apply": lambda a: 28 * a["n_chunks"] * model_bytes["adam_chunk"],       # per bucket (partial last chunks counted whole)
         "p2i_adam_step": lambda a: model_bytes["adam"].get(a["n_chunks"], 28 * a["n_chunks"] * model_bytes["adam_chunk"]),
     }
 

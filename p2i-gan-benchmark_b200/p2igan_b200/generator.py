@@ -155,12 +155,12 @@ class P2IGenerator(BaseNetwork):
         d["_wcache"] = None
         return d
 
-    def _side_stream(self, device) -> torch.cuda.Stream:
-        st = getattr(self, "_side", None)
-        if st is None or st.device != torch.device(device):
-            st = torch.cuda.Stream(device=device)
-            self._side = st
-        return st
+    def _side_stream(self, device, which: int = 0) -> torch.cuda.Stream:
+        sts = getattr(self, "_side", None)
+        if sts is None or sts[0].device != torch.device(device):
+            sts = [torch.cuda.Stream(device=device) for _ in range(2)]
+            self._side = sts
+        return sts[which]
 
     def _forward_train(self, mf, mk):
         """Forward that keeps what the backward needs. Returns (out f32 [B,16,H,W], saved dict)."""
@@ -304,7 +304,7 @@ class P2IGenerator(BaseNetwork):
         # the side stream behind the last weight gradients, next to the InputBlock backward chain.
         s = self.Convsin[0].main[0]
         dw_stem = torch.zeros(64, 4, 9, dtype=torch.float32, device=dout.device)        # allocated on the main stream
-        sside = _overlap.pick(wside, main, _overlap.G_STEMDW)
+        sside = _overlap.pick(self._side_stream(dout.device, 1), main, _overlap.G_STEMDW)   # NOT the weight-gradient stream: that one has a backlog
         dx_in = ops.stem_bwd_dx(d_stem, sv["x_in"], wc["stem"])
         sside.wait_stream(main)
         with torch.cuda.stream(sside):
@@ -320,6 +320,8 @@ class P2IGenerator(BaseNetwork):
                             tg["input.layers.0.conv.bias"], tg["input.layers.1.conv.weight"], tg["input.layers.1.conv.bias"])
         if wside is not main:
             main.wait_stream(wside)
+        if sside is not main:
+            main.wait_stream(sside)
         return fresh
 
     # (level, residual blocks) per gradient bucket, in the order the backward pass completes them.  The 512-channel level

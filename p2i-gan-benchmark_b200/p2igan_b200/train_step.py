@@ -159,6 +159,7 @@ class GANTrainStep:
         self._g_scale = 1.0 / world
         self._bucketed = (not multi or self.peer_exchange) and os.environ.get("P2I_BUCKETED", "1") != "0"
         self._adam_done = set()
+        self._armed = False
         if self._bucketed:
             self._g_named = dict(generator.named_parameters())
             generator._bucket_hook = self._on_bucket
@@ -172,6 +173,8 @@ class GANTrainStep:
             disc_bwd.prepare(discriminator)
 
     def _on_bucket(self, names, producer: torch.cuda.Stream) -> None:
+        if not self._armed:          # a backward pass outside step() (validation, user code) must not touch the parameters
+            return
         params = [self._g_named[n] for n in names]
         run_on = producer
         if self.peer_exchange:
@@ -224,7 +227,11 @@ class GANTrainStep:
         if self._bucketed:
             self._adam_done.clear()
             self.opt_g.begin_step()                      # before the backward pass forks its side streams
-        loss_g.backward()
+            self._armed = True
+        try:
+            loss_g.backward()
+        finally:
+            self._armed = False
         self._out["total"] = loss_g.detach()
         self._preds = self._loss_g = None
 

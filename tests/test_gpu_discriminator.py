@@ -126,34 +126,31 @@ def test_discriminator_frozen_params_input_grad_only():
 
 def test_forward_pair_equals_two_calls():
     """D.forward_pair(fake, real) -- the D update's two calls on two stream lanes -- must give the values, the state updates
-    (two successive power iterations) and the gradients of D(fake) followed by D(real)."""
+    (two successive power iterations) and the gradients of D(fake) followed by D(real).  Two RUNS of the sequential form are
+    not bit-identical either (the power iteration and the weight gradients sum with fp32 atomics, and a last-bit change of
+    sigma flips bf16 roundings of the packed weights), so the yardstick is the difference between two sequential runs."""
     import copy
     from p2igan_b200.losses import gan_loss
     D1, _ = _pair(64, 64)
-    D2 = copy.deepcopy(D1)
+    D2, D3 = copy.deepcopy(D1), copy.deepcopy(D1)
     frames, _, _ = synth.make_batch(2, 16, 64, 64, 12, 3)
     fake = (frames.flip(1) * 0.7).to(DEV)
     real = frames.to(DEV)
-    D1.train(); D2.train()
 
-    def loss_of(lf, lr_):
-        return 0.5 * (gan_loss(lr_, True, loss_type="hinge", is_disc=True) + gan_loss(lf, False, loss_type="hinge", is_disc=True))
+    def run(D, paired):
+        D.train()
+        f = fake.clone().requires_grad_(True)
+        lf, lr_ = D.forward_pair(f, real) if paired else (D(f), D(real))
+        loss = 0.5 * (gan_loss(lr_, True, loss_type="hinge", is_disc=True) + gan_loss(lf, False, loss_type="hinge", is_disc=True))
+        loss.backward()
+        torch.cuda.synchronize()
+        out = {"lf": lf.detach(), "lr": lr_.detach(), "dx": f.grad}
+        out.update({"g." + n: p.grad for n, p in D.named_parameters() if n != "alpha3d"})
+        out.update({k: v.clone() for k, v in D.state_dict().items() if k.endswith("weight_u") or k.endswith("weight_v")})
+        assert D.alpha3d.grad is None
+        return out
 
-    fa = fake.clone().requires_grad_(True)
-    lf1, lr1 = D1(fa), D1(real)
-    loss_of(lf1, lr1).backward()
-    fb = fake.clone().requires_grad_(True)
-    lf2, lr2 = D2.forward_pair(fb, real)
-    loss_of(lf2, lr2).backward()
-    torch.cuda.synchronize()
-    assert torch.equal(lf1, lf2) and torch.equal(lr1, lr2)            # same kernels on the same operands
-    sd1, sd2 = D1.state_dict(), D2.state_dict()
-    for k in sd1:
-        if k.endswith("weight_u") or k.endswith("weight_v"):
-            assert torch.equal(sd1[k], sd2[k]), k
-    assert rel_l2(fb.grad, fa.grad) < 1e-5
-    for (n, p1), (_, p2) in zip(D1.named_parameters(), D2.named_parameters()):
-        if n == "alpha3d":
-            assert p2.grad is None
-            continue
-        assert rel_l2(p2.grad, p1.grad) < 1e-4, n                     # fp32 atomics: summation order only
+    a, b, c = run(D1, False), run(D3, False), run(D2, True)
+    for k in a:
+        noise, diff = rel_l2(b[k], a[k]), rel_l2(c[k], a[k])
+        assert diff <= 4 * noise + 1e-6 and diff < 2e-3, (k, diff, noise)
