@@ -20,8 +20,8 @@
 namespace p2i {
 
 constexpr int PEER_MAX_RANKS = 8;
-constexpr int PEER_MAX_BLOCKS = 160;
-constexpr int PEER_THREADS = 512;
+constexpr int PEER_MAX_BLOCKS = 320;
+constexpr int PEER_THREADS = 256;
 
 struct PeerTable {
     float* buf[PEER_MAX_RANKS];      // buf[r]: rank r's flat buffer as mapped in THIS process (buf[rank] is local)
@@ -62,8 +62,12 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& a, int phase, int 
 
 // WT = world size known at compile time (2, 4, 8: the peer loop is fully unrolled so that the loads from ALL peers are in
 // flight together -- with a run-time trip count each peer's load waited for the previous peer's add) or 0 = generic.
+// Register budget: a bucket exchange runs UNDER the backward pass, next to a tensor-core CTA that holds up to ~40 k of an
+// SM's 64 k registers (384 threads x 104) -- 256 threads x <= 64 registers fit beside it, 512 x 122 (round 1's WT = 8 form)
+// would keep the conv CTA off the SM for as long as the exchange spins.  Hence 256 threads, minBlocks = 4 (<= 64 registers) and fewer
+// independent loads per peer at larger world sizes (what is in flight per thread stays 8 x 16 bytes).
 template <int WT>
-__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerTable a) {
+__global__ void __launch_bounds__(PEER_THREADS, 4) peer_allreduce_kernel(const PeerTable a) {
     const int epoch = *a.epoch;
     const int W = WT ? WT : a.world, G = gridDim.x;
     const long long n4 = a.n >> 2;
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
     const long long per4 = (shard4 + G - 1) / G;               // float4 per (shard, block)
     const long long lo = static_cast<long long>(blockIdx.x) * per4;
     const long long hi = (lo + per4 < shard4) ? lo + per4 : shard4;
-    constexpr int U = WT == 8 ? 2 : 4;                          // independent 16-byte loads per peer and thread
+    constexpr int U = WT == 8 ? 1 : (WT == 4 ? 2 : 4);          // independent 16-byte loads per peer and thread
 
     peer_barrier(a, 0, epoch);
     {
@@ -223,7 +227,7 @@ static int peer_allreduce_launch(void* const* bufs, void* const* flags, int rank
         P2I_CHECK_ARG(r >= world || (a.buf[r] && a.flags[r]), "peer_allreduce: null peer pointer for rank %d", r);
     }
     a.epoch = epoch_dev; a.err = err_dev; a.n = n; a.off4 = offset >> 2; a.rank = rank; a.world = world;
-    int grid = blocks > 0 ? blocks : sm_count();
+    int grid = blocks > 0 ? blocks : 2 * sm_count();          // whole-buffer exchange: two 256-thread CTAs per SM
     if (grid > PEER_MAX_BLOCKS) grid = PEER_MAX_BLOCKS;
     peer_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(epoch_dev);
     P2I_CHECK_LAUNCH("peer_tick_kernel");

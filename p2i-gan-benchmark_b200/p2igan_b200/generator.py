@@ -156,9 +156,11 @@ class P2IGenerator(BaseNetwork):
         return d
 
     def _side_stream(self, device, which: int = 0) -> torch.cuda.Stream:
+        """0: InputBlock / weight gradients of levels 0-2; 1: stem weight gradient; 2: weight gradients of level 3, HIGH priority
+        (its CTAs are placed before those of the lower levels' backlog when SMs free up -- see _backward_train)."""
         sts = getattr(self, "_side", None)
         if sts is None or sts[0].device != torch.device(device):
-            sts = [torch.cuda.Stream(device=device) for _ in range(2)]
+            sts = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device), torch.cuda.Stream(device=device, priority=-1)]
             self._side = sts
         return sts[which]
 
@@ -242,10 +244,18 @@ class P2IGenerator(BaseNetwork):
         wside = _overlap.pick(self._side_stream(dout.device), main, _overlap.G_WGRAD)
         keep = []
 
-        def wgrad_side(x, g, ks, out):
+        # Level 3 (512 channels) is reached last but owns 74 % of the gradient bytes: its weight gradients go to a HIGH-priority
+        # stream so that they overtake the backlog of the lower levels' weight gradients, its buckets complete right behind its
+        # data-gradient chain and their exchange / Adam update overlap the backlog instead of trailing it.
+        wside3 = _overlap.pick(self._side_stream(dout.device, 2), wside, _overlap.G_WGRAD3)
+        used = set()
+
+        def wgrad_side(x, g, ks, out, st=None):
+            st = wside if st is None else st
             keep.extend((x, g))
-            wside.wait_stream(main)
-            with torch.cuda.stream(wside):
+            st.wait_stream(main)
+            used.add(st)
+            with torch.cuda.stream(st):
                 ops.conv2d_wgrad(x, g, ks, out=out)
 
         # The DO-Conv composition backward (arena -> dW, dD) runs per BUCKET of layers, on the stream of the weight gradients,
@@ -266,18 +276,20 @@ class P2IGenerator(BaseNetwork):
                                            gviews[i].data_ptr(), tg[n + ".W"].data_ptr(), tg[n + ".D"].data_ptr(),
                                            convs[i][1].in_channels) for i, n in zip(idx, names)])
                 tabs[bi] = (key, torch.frombuffer(bytearray(tab), dtype=torch.uint8).to(dout.device))
-            with torch.cuda.stream(wside):
+            st = wside3 if level == 3 else wside
+            with torch.cuda.stream(st):
                 ops.doconv_compose_bwd(tabs[bi][1], len(idx), convs[idx[0]][1].in_channels)
             if hook is not None:
-                hook([n + sfx for n in names for sfx in (".W", ".D")], wside)
+                hook([n + sfx for n in names for sfx in (".W", ".D")], st)
 
         def eblock_bwd(level, d):
             base = level * 2 * self.num_res
             for r in reversed(range(self.num_res)):
                 a, y = sv["res"][level][r]
-                wgrad_side(y, d, 3, gviews[base + 2 * r + 1])
+                st = wside3 if level == 3 else None
+                wgrad_side(y, d, 3, gviews[base + 2 * r + 1], st)
                 dy = ops.conv2d_cl(d, bufs_t[base + 2 * r + 1], None, False, mask=y)
-                wgrad_side(a, dy, 3, gviews[base + 2 * r])
+                wgrad_side(a, dy, 3, gviews[base + 2 * r], st)
                 d = ops.conv2d_cl(dy, bufs_t[base + 2 * r], d, False)
                 for bi, (lv, blocks) in enumerate(buckets):
                     if lv == level and min(blocks) == r:        # blocks are visited in descending order: r closes the bucket
@@ -318,10 +330,9 @@ class P2IGenerator(BaseNetwork):
         w0, b0, w1, b1 = (p.detach().contiguous() for p in self.input.gate_params())
         ops.gate_points_bwd(inp, pts, counts, w0, b0, w1, b1, dvals, tg["input.layers.0.conv.weight"],
                             tg["input.layers.0.conv.bias"], tg["input.layers.1.conv.weight"], tg["input.layers.1.conv.bias"])
-        if wside is not main:
-            main.wait_stream(wside)
-        if sside is not main:
-            main.wait_stream(sside)
+        for st in used | {wside, sside}:
+            if st is not main:
+                main.wait_stream(st)
         return fresh
 
     # (level, residual blocks) per gradient bucket, in the order the backward pass completes them.  The 512-channel level

@@ -56,11 +56,11 @@ class FlatGrads:
 
     # ---- bucketed exchange (peer mode): ranges of the buffer are summed over the ranks on a side stream as soon as the
     # backward pass has finalised them; finish() exchanges whatever is left and joins the side stream.
-    BUCKET_BLOCKS = int(os.environ.get("P2I_PEER_BLOCKS", "32"))     # CTAs of a bucket exchange: few enough to co-reside with GEMMs
+    BUCKET_BLOCKS = int(os.environ.get("P2I_PEER_BLOCKS", "64"))     # CTAs of a bucket exchange: few enough to co-reside with GEMMs
 
     def comm_stream(self) -> torch.cuda.Stream:
         if self._comm is None:
-            self._comm = torch.cuda.Stream(device=self.flat.device)
+            self._comm = torch.cuda.Stream(device=self.flat.device, priority=-1)     # exchange CTAs are placed as soon as a slot frees
         return self._comm
 
     def exchange_params(self, params, producer: torch.cuda.Stream) -> bool:
@@ -157,7 +157,13 @@ class GANTrainStep:
         # the rest of the backward pass.  Not with the NCCL exchange (the gradients are only summed after the backward pass).
         world = dist.get_world_size(process_group) if multi else 1
         self._g_scale = 1.0 / world
-        self._bucketed = (not multi or self.peer_exchange) and os.environ.get("P2I_BUCKETED", "1") != "0"
+        # 1 GPU: always (the bucket's Adam update hides under the backward pass).  N GPUs, peer exchange: opt-in with
+        # P2I_BUCKETED=1 -- measured SLOWER at N = 2 (6.52 vs 6.34 ms/step, profiles/r2_bucketed_exchange.txt): level 3 holds 74 % of
+        # the bytes and completes last, an exchange that co-resides with the tensor-core CTAs is limited to ~64 registers x 256
+        # threads per CTA and no shared memory (100-130 GB/s per 19 MB bucket against 500 GB/s for the full-width kernel), and
+        # its CTAs slow the latency-bound kernels they share SMs with.
+        self._bucketed = (not multi and os.environ.get("P2I_BUCKETED", "1") != "0") or \
+            (multi and self.peer_exchange and os.environ.get("P2I_BUCKETED", "0") == "1")
         self._adam_done = set()
         self._armed = False
         if self._bucketed:

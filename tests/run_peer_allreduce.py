@@ -160,11 +160,14 @@ def dp_equivalence():
         return ts, out, ts.flat_g.flat[:ts.flat_g.n].clone(), ts.flat_d.flat[:ts.flat_d.n].clone()
 
     _, l1, g1, d1 = run(full, process_group=solo)
+    os.environ["P2I_BUCKETED"] = "1"            # the bucketed form is opt-in for N > 1 (train_step.py); exercise it here
     ts, lp, gp, dp = run(mine, peer_exchange=True)
     assert ts.peer_exchange and getattr(ts.G, "_bucket_hook", None) is not None
     for name, a_, b_ in (("G", gp / world, g1), ("D", dp / world, d1)):
         rel = float((a_ - b_).norm() / b_.norm())
-        assert rel < 2e-3, (name, rel)          # bf16 activations are identical per event; wgrad atomics reorder fp32 sums
+        # activations are per event, but run-to-run noise of the step itself is ~2e-3 (fp32 atomics reorder the power iteration
+        # and the weight gradients; a last-bit change of sigma flips bf16 roundings).  A lost bucket or a wrong 1/world would be O(1).
+        assert rel < 1e-2, (name, rel)
     for k in ("rec", "pool", "dis"):
         t = torch.tensor([lp[k]], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
@@ -179,6 +182,11 @@ def dp_equivalence():
     ref_ = fp.clone()
     dist.broadcast(ref_, 0)
     assert torch.equal(ref_, fp), "parameters diverged across ranks after graph replays"
+    os.environ["P2I_BUCKETED"] = "0"
+    ts0, l0, g0, d0 = run(mine, peer_exchange=True)          # default form: one whole-buffer exchange after the backward pass
+    assert getattr(ts0.G, "_bucket_hook", None) is None
+    rel = float((g0 / world - g1).norm() / g1.norm())
+    assert rel < 1e-2, ("G unbucketed", rel)
 
 
 dp_equivalence()

@@ -17,6 +17,10 @@ for s in $steps; do
     pdl1) P2I_PDL=1 timeout 600 python bench.py --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_pdl1.json 2> gpurun_out/${tag}_bench_pdl1.err; echo "pdl1 rc=$?"; head -c 300 gpurun_out/${tag}_bench_pdl1.json;;
     testsel) timeout 900 python -m pytest tests -m gpu -q -rf -p no:cacheprovider -k "$P2I_TESTSEL" > gpurun_out/${tag}_pytest_sel.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_sel.txt; tail -30 gpurun_out/${tag}_pytest_sel.txt;;
     peer2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_peer_allreduce.py > gpurun_out/${tag}_peer2.txt 2>&1; echo "peer2 rc=$?"; tail -15 gpurun_out/${tag}_peer2.txt;;
+    bench2) for b in 1 0; do P2I_BUCKETED=$b timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2953$b bench.py --gpus 2 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_2gpu_bucketed$b.json 2> gpurun_out/${tag}_bench_2gpu_bucketed$b.err; echo "bench2 bucketed=$b rc=$?"; head -c 300 gpurun_out/${tag}_bench_2gpu_bucketed$b.json; echo; done;;
+    graph2) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/prof_graph.py gpurun_out/${tag}_graph2_timeline.txt > gpurun_out/${tag}_graph2_kernels.txt 2>&1; echo "graph2 rc=$?"; grep "^kernels" gpurun_out/${tag}_graph2_kernels.txt;;
+    blocks2) for nb in 8 16 64; do P2I_PEER_BLOCKS=$nb timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2957${nb:0:1} bench.py --gpus 2 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_2gpu_blocks$nb.json 2> gpurun_out/${tag}_bench_2gpu_blocks$nb.err; echo "blocks=$nb rc=$?"; head -c 250 gpurun_out/${tag}_bench_2gpu_blocks$nb.json; echo; done;;
+    bench8) for b in 1 0; do P2I_BUCKETED=$b timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2954$b bench.py --gpus 8 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_8gpu_bucketed$b.json 2> gpurun_out/${tag}_bench_8gpu_bucketed$b.err; echo "bench8 bucketed=$b rc=$?"; head -c 300 gpurun_out/${tag}_bench_8gpu_bucketed$b.json; echo; done;;
     benchq) timeout 600 python bench.py --steps 50 --no-cpu --no-extras > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err; echo "benchq rc=$?"; head -c 400 gpurun_out/${tag}_bench_quick.json;;
     infer) timeout 600 python bench.py --workload infer --steps 100 --no-extras > gpurun_out/${tag}_bench_infer.json 2> gpurun_out/${tag}_bench_infer.err; echo "infer rc=$?";;
     ref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?";;

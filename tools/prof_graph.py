@@ -12,20 +12,31 @@ from p2igan_b200 import build_discriminator, build_generator
 from p2igan_b200.train_step import GANTrainStep, GraphedStep
 from torch.profiler import ProfilerActivity, profile
 
-dev = "cuda:0"
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+if world > 1:                      # data-parallel step under torchrun: peer-memory exchange, rank 0 reports
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
 cfg = synth.make_cfg(128, 128)
 torch.manual_seed(2024)
 G = build_generator(cfg).to(dev).train()
 D = build_discriminator(cfg).to(dev).train()
-ts = GANTrainStep(cfg, G, D)
-batch = tuple(t.to(dev) for t in synth.make_batch(16, 16, 128, 128, 79, 1))
+ts = GANTrainStep(cfg, G, D, peer_exchange=world > 1)
+batch = tuple(t.to(dev) for t in synth.make_batch(16, 16, 128, 128, 79, 1 + rank))
 gs = GraphedStep(lambda a, b, c: ts.step(a, b, c)["total"], batch, warmup=3)
 for _ in range(3):
     gs(*batch)
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     gs(*batch)
     torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 ev = [e for e in prof.events() if e.device_type.name == "CUDA"]
 ev.sort(key=lambda e: e.time_range.start)
 busy = sum(e.time_range.end - e.time_range.start for e in ev)
@@ -48,3 +59,6 @@ if len(sys.argv) > 1:
     with open(sys.argv[1], "w") as f:
         for e in ev:
             f.write(f"{(e.time_range.start - t0):10.2f} {(e.time_range.end - e.time_range.start):8.2f} s{getattr(e, 'device_resource_id', -1)} {e.name.split('(')[0][:70]}\n")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
