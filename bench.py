@@ -556,6 +556,23 @@ class Workload:
         self.run = self.graphed if self.graphed is not None else eager
         self._dist = dist
         self._e2e_ready = False
+        # Inference end to end: what crosses PCIe is what the reference's loader reads from disk -- uint8 frames -- plus ONE
+        # static uint8 gauge mask; STIDataset.post_process (/255, mask multiply; sti_dataset.py:203-229) runs on the device
+        # (p2igan_b200.prepare_batch_u8, bit-exact vs the reference's own post_process: tests/test_gpu_trainer.py).  12x less
+        # H2D than three fp32 tensors, which is what keeps 8 GPUs behind one host from starving.
+        self.u8 = not self.train
+        if self.u8:
+            from p2igan_b200 import prepare_batch_u8
+            g = torch.Generator().manual_seed(77 + rank)
+            self.host_u8 = [torch.randint(0, 256, (B, T, HW, HW), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.host_mask_u8 = (self.batches[0][2][0, 0, 0] > 0).to(torch.uint8).cpu().pin_memory()
+            ex = (self.host_u8[0].to(dev), self.host_mask_u8.to(dev))
+
+            def eager_u8(fr_u8, mk_u8):
+                _, mf, mk = prepare_batch_u8(fr_u8, mk_u8, HW, HW)
+                with torch.no_grad():
+                    return G(mf, mk)
+            self.run_u8 = GraphedStep(eager_u8, ex, warmup=2) if use_graph else eager_u8
 
     def barrier(self):
         if self.world > 1:
@@ -571,7 +588,10 @@ class Workload:
         dev = self.dev
         self.main = torch.cuda.current_stream()
         self.s_h2d, self.s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-        self.stage_in = [tuple(torch.empty_like(t) for t in self.batches[0]) for _ in range(2)]
+        if self.u8:
+            self.stage_in = [(torch.empty_like(self.host_u8[0], device=dev), torch.empty_like(self.host_mask_u8, device=dev)) for _ in range(2)]
+        else:
+            self.stage_in = [tuple(torch.empty_like(t) for t in self.batches[0]) for _ in range(2)]
         self.stage_out = [torch.empty(self.res_shape, dtype=torch.float32, device=dev) for _ in range(2)]
         mk = lambda: [torch.cuda.Event() for _ in range(2)]       # noqa: E731
         self.ev_in_ready, self.ev_in_free, self.ev_out_ready, self.ev_out_free = mk(), mk(), mk(), mk()
@@ -581,11 +601,15 @@ class Workload:
         k = i % 2
         with torch.cuda.stream(self.s_h2d):
             self.s_h2d.wait_event(self.ev_in_free[k])
-            for j in ((0, 1, 2) if self.train else (1, 2)):       # inference reads masked_frames and masks only
-                self.stage_in[k][j].copy_(self.host[k][j], non_blocking=True)
+            if self.u8:
+                self.stage_in[k][0].copy_(self.host_u8[k], non_blocking=True)
+                self.stage_in[k][1].copy_(self.host_mask_u8, non_blocking=True)
+            else:
+                for j in (0, 1, 2):
+                    self.stage_in[k][j].copy_(self.host[k][j], non_blocking=True)
             self.ev_in_ready[k].record(self.s_h2d)
         self.main.wait_event(self.ev_in_ready[k])
-        o = self.run(*self.stage_in[k])                  # graphed: one D2D copy into the static inputs + replay
+        o = (self.run_u8 if self.u8 else self.run)(*self.stage_in[k])     # graphed: one D2D copy into the static inputs + replay
         self.ev_in_free[k].record(self.main)
         self.main.wait_event(self.ev_out_free[k])
         self.stage_out[k].copy_(o.reshape(self.res_shape), non_blocking=True)
@@ -601,7 +625,7 @@ class Workload:
 
     def io_bytes(self):
         px = self.B * T * self.HW * self.HW * 4
-        return (3 * px, 6 * 4) if self.train else (2 * px, px)
+        return (3 * px, 6 * 4) if self.train else (px // 4 + self.HW * self.HW, px)      # inference: uint8 frames + one uint8 mask in
 
     def time_steps(self, steps, warmup):
         """(ms over exactly `steps` steps, wall t0, wall t1): CUDA events, barrier + synchronize on both sides."""
@@ -664,7 +688,8 @@ def sub_record(name, args, world, rank, dev, steps):
     ev = w.B * world * steps
     rec = {"metric": w.metric, "baseline_config": f"configs[{w.cfg_index}]", "workload": w.desc, "value": ev / (ms * 1e-3),
            "unit": "events/s", "steps": steps, "ms_per_step": ms / steps, "events_per_step_per_gpu": w.B,
-           "e2e": {"value": ev / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "e2e": {"value": ev / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "inputs": "fp32 frames / masked / masks" if w.train else "uint8 frames + static uint8 mask, prepare_batch_u8 on the device"},
            "losses_last_step": w.check_loss_finite()}
     if name == "stress256":
         rec["metrics_sweep"] = metrics_sweep(dev)
@@ -832,6 +857,9 @@ def run_ours(args):
                        "weights": "random init seed 2024",
                        "launch": "eager" if w.graphed is None else ("3 CUDA graphs + 2 NCCL all-reduces per step" if (world > 1 and train and w.exchange != "peer") else "CUDA graph replay"),
                        "e2e_pipeline": "H2D / step / D2H on three streams, double-buffered",
+                       "e2e_inputs": ("three fp32 tensors (frames, masked, masks) from pinned host memory" if train else
+                                      "uint8 frames + one static uint8 gauge mask from pinned host memory; /255 and the mask multiply "
+                                      "(STIDataset.post_process) run on the device (prepare_batch_u8); fp32 result back"),
                        "parallelism": ((f"data parallel over {world} GPU(s): flat D and G gradient buffers, " +
                                         ("NVLink peer-memory all-reduce kernel (CUDA IPC) inside the step graph" if w.exchange == "peer"
                                          else ("NCCL all-reduce" if world > 1 else "no exchange at 1 GPU"))) if train

@@ -404,40 +404,58 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
 // then sit in different frames / far-apart rows and hit distinct points; each lane still streams through consecutive
 // addresses, so its 32-byte sectors are reused from L1 on the following iterations.
 constexpr int IDW_BWD_SPAN = 64;       // offsets per block: 128 x B blocks at 16x128x128 (512 gave 16 x B blocks: latency-bound, 106-330 us)
+// Shared-memory float atomics are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN; so are the 64-bit integer ones), so the
+// kernel issues as few of them as it can: a lane walks a run of IDW_BWD_RUN CONSECUTIVE queries (one row segment), whose
+// 4-neighbour sets change only every few pixels, and keeps the last four (point, partial sum) pairs in registers -- an
+// atomic is issued only when a point drops out of that window (about 6x fewer than one per query and neighbour).  The
+// sums are still privatised per block in shared memory (one global RED per touched point and block).
+constexpr int IDW_BWD_RUN = 32;                        // queries per lane; a block covers 256 * 32 = 8192 consecutive queries
+constexpr int IDW_BWD_PTS = 8192;
 __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
                                                              const float* __restrict__ nbr_w, const int* __restrict__ counts,
                                                              const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
-    __shared__ float acc[IDW_SMEM_PTS];
+    __shared__ float acc[IDW_BWD_PTS];
     const int b = blockIdx.y;
     const int N = counts[b];
     if (N == 0) return;
-    const bool priv = N <= IDW_SMEM_PTS;
+    const bool priv = N <= IDW_BWD_PTS;
     if (priv)
         for (int i = threadIdx.x; i < N; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
     const int sb = src ? src[b] : b;
     float* v = dvals + static_cast<size_t>(b) * cap;
     float* dst = priv ? acc : v;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int R = (Q + 31) >> 5;
-    const int off0 = blockIdx.x * IDW_BWD_SPAN + warp * (IDW_BWD_SPAN / 8);
+    const int q0 = (blockIdx.x * 256 + threadIdx.x) * IDW_BWD_RUN;
     const int4* idp = reinterpret_cast<const int4*>(nbr_idx) + static_cast<size_t>(sb) * Q;
     const float4* wp = reinterpret_cast<const float4*>(nbr_w) + static_cast<size_t>(sb) * Q;
     const float* gp = dout + static_cast<size_t>(b) * Q;
-#pragma unroll 4
-    for (int it = 0; it < IDW_BWD_SPAN / 8; ++it) {
-        const int off = off0 + it;
-        const int q = lane * R + off;
-        if (off >= R || q >= Q) continue;
+    int s0 = -1, s1 = -1, s2 = -1, s3 = -1;            // FIFO window of points with partial sums a0..a3
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    auto add = [&](int id, float val) {
+        if (id == s3) { a3 += val; return; }
+        if (id == s2) { a2 += val; return; }
+        if (id == s1) { a1 += val; return; }
+        if (id == s0) { a0 += val; return; }
+        if (s0 >= 0 && a0 != 0.f) atomicAdd(dst + s0, a0);
+        s0 = s1; a0 = a1; s1 = s2; a1 = a2; s2 = s3; a2 = a3; s3 = id; a3 = val;
+    };
+#pragma unroll 2
+    for (int it = 0; it < IDW_BWD_RUN; ++it) {
+        const int q = q0 + it;
+        if (q >= Q) break;
         const float g = __ldg(gp + q);
         if (g == 0.f) continue;
         const int4 id = __ldg(idp + q);
         const float4 w = __ldg(wp + q);
-        if (w.x != 0.f) atomicAdd(dst + id.x, w.x * g);
-        if (w.y != 0.f) atomicAdd(dst + id.y, w.y * g);
-        if (w.z != 0.f) atomicAdd(dst + id.z, w.z * g);
-        if (w.w != 0.f) atomicAdd(dst + id.w, w.w * g);
+        if (w.x != 0.f) add(id.x, w.x * g);
+        if (w.y != 0.f) add(id.y, w.y * g);
+        if (w.z != 0.f) add(id.z, w.z * g);
+        if (w.w != 0.f) add(id.w, w.w * g);
     }
+    if (s0 >= 0 && a0 != 0.f) atomicAdd(dst + s0, a0);
+    if (s1 >= 0 && a1 != 0.f) atomicAdd(dst + s1, a1);
+    if (s2 >= 0 && a2 != 0.f) atomicAdd(dst + s2, a2);
+    if (s3 >= 0 && a3 != 0.f) atomicAdd(dst + s3, a3);
     if (priv) {
         __syncthreads();
         for (int i = threadIdx.x; i < N; i += blockDim.x)
@@ -541,7 +559,7 @@ extern "C" int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const floa
                                const int* src, float* dvals, int cap, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dout && nbr_idx && nbr_w && counts && dvals, "idw_knn_bwd: null pointer");
     const int Q = T * H * W;
-    dim3 grid(cdiv((Q + 31) / 32, IDW_BWD_SPAN), B);
+    dim3 grid(cdiv(Q, 256 * IDW_BWD_RUN), B);
     idw_interp_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, nbr_idx, nbr_w, counts, src, cap, dvals, Q);
     P2I_CHECK_LAUNCH("idw_interp_bwd_kernel");
     return P2I_OK;

@@ -22,20 +22,22 @@ struct MetricParams {
     int apply_transform;        // regression sums on transformed values?
 };
 
-__device__ __forceinline__ float rain(float x) { return powf(10.f, x * 0.0625f) * 0.036f; }
+// R = 0.036 * 10^(x/16) (metric.py:16-20) as one exp2: 10^(x/16) = 2^(x * log2(10)/16)
+__device__ __forceinline__ float rain(float x) { return exp2f(x * 0.20762050593046f) * 0.036f; }
 
 // acc layout (double): [0] abs_sum [1] sq_sum | [2 + 4*t + {0..3}] hits, misses, false, correct |
 //                      [18 + 2*(t*4+s) + {0,1}] fss numerator sum, denominator sum
 __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                                       double* __restrict__ acc, const MetricParams p) {
     __shared__ unsigned long long sm[MS * MS];     // per pixel: byte lane 2*t = pred mask, 2*t+1 = target mask (threshold t)
-    __shared__ float red[8][34];
+    __shared__ unsigned long long hs[3][MS * MT];  // horizontal box sums of widths 2 / 4 / 8 (staged row x tile column)
+    __shared__ float red[8][50];
     const int n = blockIdx.z;
     const int oy0 = blockIdx.y * MT, ox0 = blockIdx.x * MT;
     const float* P = pred + static_cast<size_t>(n) * p.H * p.W;
     const float* Tg = target + static_cast<size_t>(n) * p.H * p.W;
     float a_abs = 0.f, a_sq = 0.f;
-    float cont[4][4];
+    float cont[4][4];                              // [threshold][hits, misses, false alarms, correct negatives]: static indices only
     float fs[16][2];
 #pragma unroll
     for (int t = 0; t < 4; ++t)
@@ -58,7 +60,12 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
                     const bool a = pr >= p.thr[t], o = tr >= p.thr[t];
                     bits |= (a ? 1ull : 0ull) << (16 * t);
                     bits |= (o ? 1ull : 0ull) << (16 * t + 8);
-                    if (own) cont[t][(a ? 0 : 1) + (o ? 0 : 2) == 0 ? 0 : ((!a && o) ? 1 : ((a && !o) ? 2 : 3))] += 1.f;
+                    if (own) {
+                        cont[t][0] += (a && o) ? 1.f : 0.f;
+                        cont[t][1] += (!a && o) ? 1.f : 0.f;
+                        cont[t][2] += (a && !o) ? 1.f : 0.f;
+                        cont[t][3] += (!a && !o) ? 1.f : 0.f;
+                    }
                 }
             }
             if (own) {
@@ -70,22 +77,29 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
         sm[e] = bits;
     }
     __syncthreads();
+    // separable box sums of the packed masks (byte lanes never overflow: at most 64 pixels per box): horizontal sums of
+    // widths 2 / 4 / 8 per staged row (8 shared-memory loads), then vertical sums (14 loads) -- 64 loads per output before
+    for (int e = threadIdx.x; e < MS * MT; e += blockDim.x) {
+        const int sy = e / MT, tx = e - sy * MT;
+        const unsigned long long* r = sm + sy * MS + tx + MH;
+        const unsigned long long h2 = r[-1] + r[0];
+        const unsigned long long h4 = h2 + r[-2] + r[1];
+        const unsigned long long h8 = h4 + r[-4] + r[-3] + r[2] + r[3];
+        hs[0][e] = h2; hs[1][e] = h4; hs[2][e] = h8;
+    }
+    __syncthreads();
     // every thread owns 4 output positions of the tile
     for (int e = threadIdx.x; e < MT * MT; e += blockDim.x) {
         const int ty = e / MT, tx = e - ty * MT;
         const int oy = oy0 + ty, ox = ox0 + tx;
         if (oy > p.H || ox > p.W) continue;
         const int cy = ty + MH, cx = tx + MH;                 // staged coordinate of input pixel (oy, ox)
-        unsigned long long c2 = 0ull, c4 = 0ull, c8 = 0ull;
-#pragma unroll
-        for (int dy = -4; dy < 4; ++dy)
-#pragma unroll
-            for (int dx = -4; dx < 4; ++dx) {
-                const unsigned long long v = sm[(cy + dy) * MS + cx + dx];
-                c8 += v;
-                if (dy >= -2 && dy < 2 && dx >= -2 && dx < 2) c4 += v;
-                if (dy >= -1 && dy < 1 && dx >= -1 && dx < 1) c2 += v;
-            }
+        const unsigned long long* c = &hs[0][cy * MT + tx];
+        const unsigned long long c2 = c[-MT] + c[0];
+        c = &hs[1][cy * MT + tx];
+        const unsigned long long c4 = c[-2 * MT] + c[-MT] + c[0] + c[MT];
+        c = &hs[2][cy * MT + tx];
+        const unsigned long long c8 = c[-4 * MT] + c[-3 * MT] + c[-2 * MT] + c[-MT] + c[0] + c[MT] + c[2 * MT] + c[3 * MT];
         const unsigned long long c1 = sm[cy * MS + cx];
         const bool in1 = (oy < p.H && ox < p.W);              // k = 1 has an H x W output domain
 #pragma unroll
@@ -93,13 +107,13 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
             if (s >= p.n_scale) continue;
             const int k = p.scale[s];
             if (k == 1 && !in1) continue;
-            const unsigned long long c = (k == 1) ? c1 : (k == 2 ? c2 : (k == 4 ? c4 : c8));
+            const unsigned long long cc = (k == 1) ? c1 : (k == 2 ? c2 : (k == 4 ? c4 : c8));
             const float inv = 1.f / static_cast<float>(k * k);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 if (t >= p.n_thr) continue;
-                const float a = static_cast<float>((c >> (16 * t)) & 0xffull) * inv;
-                const float b = static_cast<float>((c >> (16 * t + 8)) & 0xffull) * inv;
+                const float a = static_cast<float>((cc >> (16 * t)) & 0xffull) * inv;
+                const float b = static_cast<float>((cc >> (16 * t + 8)) & 0xffull) * inv;
                 fs[t * 4 + s][0] += (a - b) * (a - b);
                 fs[t * 4 + s][1] += a * a + b * b;
             }
@@ -115,22 +129,17 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
         for (int k = 0; k < 4; ++k) vals[2 + 4 * t + k] = cont[t][k];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { vals[18 + 2 * i] = fs[i][0]; vals[19 + 2 * i] = fs[i][1]; }
-    for (int base = 0; base < 50; base += 34) {
-        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 34; ++j) {
-            if (base + j < 50) {
-                const float r = warp_sum(vals[base + j]);
-                if (lane == 0) red[warp][j] = r;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 34 && base + threadIdx.x < 50) {
-            float r = 0.f;
+    for (int j = 0; j < 50; ++j) {
+        const float r = warp_sum(vals[j]);
+        if (lane == 0) red[warp][j] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 50) {
+        float r = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) r += red[w8][threadIdx.x];
-            if (r != 0.f) atomicAdd(&acc[base + threadIdx.x], static_cast<double>(r));
-        }
+        for (int w8 = 0; w8 < 8; ++w8) r += red[w8][threadIdx.x];
+        if (r != 0.f) atomicAdd(&acc[threadIdx.x], static_cast<double>(r));
     }
 }
 

@@ -31,11 +31,21 @@ for s in $steps; do
     wgradab) timeout 600 python tools/bench_wgrad.py > gpurun_out/${tag}_wgrad_ab.txt 2>&1; echo "wgradab rc=$?";;
     ncu)
       timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err &&
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1600 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
           python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_list.log 2>&1
       echo "ncu list rc=$?"
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_wgrad|conv_halo" -s 640 -c ${P2I_NCU_COUNT:-24} -o gpurun_out/${tag}_conv_full \
-          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_full.log 2>&1
-      echo "ncu full rc=$?";;
+      # the 35 tensor-core launches of one generator forward (all four levels: <128,false,2> <256,false,2> <128,true,2> <64,true,1>)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 330 -c 36 -o gpurun_out/${tag}_halo_full \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_halo.log 2>&1
+      echo "ncu halo rc=$?"
+      ncu -i gpurun_out/${tag}_halo_full.ncu-rep --page raw --csv > /tmp/halo_raw.csv 2>/dev/null && python tools/ncu_summarize.py /tmp/halo_raw.csv gpurun_out/${tag}_halo_full_summary.txt
+      mv gpurun_out/${tag}_halo_full.ncu-rep /tmp/ 2>/dev/null
+      # weight gradients: the last discriminator ones, then the generator's level-0 / level-1 launches
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad -s 155 -c 22 -o gpurun_out/${tag}_wgrad_full \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_wgrad.log 2>&1
+      echo "ncu wgrad rc=$?"
+      ncu -i gpurun_out/${tag}_wgrad_full.ncu-rep --page raw --csv > /tmp/wgrad_raw.csv 2>/dev/null && python tools/ncu_summarize.py /tmp/wgrad_raw.csv gpurun_out/${tag}_wgrad_full_summary.txt
+      mv gpurun_out/${tag}_wgrad_full.ncu-rep /tmp/ 2>/dev/null
+      du -sh gpurun_out;;
   esac
 done
