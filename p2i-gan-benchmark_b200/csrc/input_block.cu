@@ -397,20 +397,29 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
     out[static_cast<size_t>(b) * Q + q] = r;
 }
 
-// dvals[b, idx] += w * dout, privatised in shared memory when the sample has at most IDW_SMEM_PTS points (one global
-// atomic per touched point per block).  Shared-memory float atomics are compare-and-swap loops, and neighbouring
-// queries share neighbours, so the lanes of a warp must NOT walk adjacent queries: lane l owns the contiguous run
-// [l*R, (l+1)*R), R = Q/32 (half a frame at 16x128x128), and a block covers IDW_BWD_SPAN offsets of every run.  Lanes
-// then sit in different frames / far-apart rows and hit distinct points; each lane still streams through consecutive
-// addresses, so its 32-byte sectors are reused from L1 on the following iterations.
-constexpr int IDW_BWD_SPAN = 64;       // offsets per block: 128 x B blocks at 16x128x128 (512 gave 16 x B blocks: latency-bound, 106-330 us)
+// dvals[b, idx] += w * dout (backward of the interpolation; reference: autograd through layer.py:284-291).
 // Shared-memory float atomics are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN; so are the 64-bit integer ones), so the
-// kernel issues as few of them as it can: a lane walks a run of IDW_BWD_RUN CONSECUTIVE queries (one row segment), whose
-// 4-neighbour sets change only every few pixels, and keeps the last four (point, partial sum) pairs in registers -- an
-// atomic is issued only when a point drops out of that window (about 6x fewer than one per query and neighbour).  The
-// sums are still privatised per block in shared memory (one global RED per touched point and block).
-constexpr int IDW_BWD_RUN = 32;                        // queries per lane; a block covers 256 * 32 = 8192 consecutive queries
+// kernel issues as few of them as it can.  Lanes of a warp take 32 CONSECUTIVE queries (coalesced loads); their k-th
+// neighbours form a few runs of equal point indices (the 4-neighbour set changes every few pixels), which are summed with a
+// segmented warp scan; only the last lane of a run issues an atomic (about 6x fewer than one per query and neighbour).
+// The sums are still privatised per block in shared memory (one global RED per touched point and block).
 constexpr int IDW_BWD_PTS = 8192;
+constexpr int IDW_BWD_ITERS = 8;                       // 32-query groups per warp: a block covers 8 * 8 * 32 = 2048 queries
+
+__device__ __forceinline__ void idw_run_add(float* dst, int id, float val, int lane) {
+    // runs of equal ids among adjacent lanes: head flags -> start lane of my run -> inclusive segmented scan of val
+    const int up = __shfl_up_sync(0xffffffffu, id, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || up != id);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, val, d);
+        if (lane - d >= start) val += o;
+    }
+    const int down = __shfl_down_sync(0xffffffffu, id, 1);
+    if ((lane == 31 || down != id) && id >= 0 && val != 0.f) atomicAdd(dst + id, val);
+}
+
 __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
                                                              const float* __restrict__ nbr_w, const int* __restrict__ counts,
                                                              const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
@@ -425,37 +434,29 @@ __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __rest
     const int sb = src ? src[b] : b;
     float* v = dvals + static_cast<size_t>(b) * cap;
     float* dst = priv ? acc : v;
-    const int q0 = (blockIdx.x * 256 + threadIdx.x) * IDW_BWD_RUN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int4* idp = reinterpret_cast<const int4*>(nbr_idx) + static_cast<size_t>(sb) * Q;
     const float4* wp = reinterpret_cast<const float4*>(nbr_w) + static_cast<size_t>(sb) * Q;
     const float* gp = dout + static_cast<size_t>(b) * Q;
-    int s0 = -1, s1 = -1, s2 = -1, s3 = -1;            // FIFO window of points with partial sums a0..a3
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    auto add = [&](int id, float val) {
-        if (id == s3) { a3 += val; return; }
-        if (id == s2) { a2 += val; return; }
-        if (id == s1) { a1 += val; return; }
-        if (id == s0) { a0 += val; return; }
-        if (s0 >= 0 && a0 != 0.f) atomicAdd(dst + s0, a0);
-        s0 = s1; a0 = a1; s1 = s2; a1 = a2; s2 = s3; a2 = a3; s3 = id; a3 = val;
-    };
+    const int q0 = (blockIdx.x * 8 + warp) * (IDW_BWD_ITERS * 32);
 #pragma unroll 2
-    for (int it = 0; it < IDW_BWD_RUN; ++it) {
-        const int q = q0 + it;
-        if (q >= Q) break;
-        const float g = __ldg(gp + q);
-        if (g == 0.f) continue;
-        const int4 id = __ldg(idp + q);
-        const float4 w = __ldg(wp + q);
-        if (w.x != 0.f) add(id.x, w.x * g);
-        if (w.y != 0.f) add(id.y, w.y * g);
-        if (w.z != 0.f) add(id.z, w.z * g);
-        if (w.w != 0.f) add(id.w, w.w * g);
+    for (int it = 0; it < IDW_BWD_ITERS; ++it) {
+        const int q = q0 + it * 32 + lane;
+        if (q0 + it * 32 >= Q) break;                  // warp-uniform
+        float g = 0.f;
+        int4 id = make_int4(-1, -1, -1, -1);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < Q) {
+            g = __ldg(gp + q);
+            id = __ldg(idp + q);
+            w = __ldg(wp + q);
+        }
+        if (__ballot_sync(0xffffffffu, g != 0.f) == 0u) continue;
+        idw_run_add(dst, (w.x != 0.f && g != 0.f) ? id.x : -1, w.x * g, lane);
+        idw_run_add(dst, (w.y != 0.f && g != 0.f) ? id.y : -1, w.y * g, lane);
+        idw_run_add(dst, (w.z != 0.f && g != 0.f) ? id.z : -1, w.z * g, lane);
+        idw_run_add(dst, (w.w != 0.f && g != 0.f) ? id.w : -1, w.w * g, lane);
     }
-    if (s0 >= 0 && a0 != 0.f) atomicAdd(dst + s0, a0);
-    if (s1 >= 0 && a1 != 0.f) atomicAdd(dst + s1, a1);
-    if (s2 >= 0 && a2 != 0.f) atomicAdd(dst + s2, a2);
-    if (s3 >= 0 && a3 != 0.f) atomicAdd(dst + s3, a3);
     if (priv) {
         __syncthreads();
         for (int i = threadIdx.x; i < N; i += blockDim.x)
@@ -559,7 +560,7 @@ extern "C" int p2i_idw_knn_bwd(const float* dout, const int* nbr_idx, const floa
                                const int* src, float* dvals, int cap, int B, int T, int H, int W, void* stream) {
     P2I_CHECK_ARG(dout && nbr_idx && nbr_w && counts && dvals, "idw_knn_bwd: null pointer");
     const int Q = T * H * W;
-    dim3 grid(cdiv(Q, 256 * IDW_BWD_RUN), B);
+    dim3 grid(cdiv(Q, 8 * IDW_BWD_ITERS * 32), B);
     idw_interp_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, nbr_idx, nbr_w, counts, src, cap, dvals, Q);
     P2I_CHECK_LAUNCH("idw_interp_bwd_kernel");
     return P2I_OK;

@@ -156,4 +156,7 @@ def test_forward_pair_equals_two_calls():
         # gradients that are sums of nearly cancelling terms (the scalar d2d.8 bias: +0.5/N per active fake logit, -0.5/N per
         # active real logit) are compared absolutely: the two lanes' atomics interleave, which reorders that fp32 sum
         small = float((c[k].double() - a[k].double()).abs().max()) <= 1e-6
-        assert small or (diff <= 4 * noise + 1e-6 and diff < 5e-2), (k, diff, noise)
+        # logits / u / v: a handful of bf16 flips of packed weights moves the logits by 1e-5 .. 3e-4 from run to run (heavy-tailed,
+        # so ONE sequential pair is a weak yardstick): fixed bound 1e-3 -- a race (a stale tile, a missing dependency) shows as O(0.1)
+        bound = max(20 * noise, 1e-3) if k in ("lf", "lr") or k.endswith(("weight_u", "weight_v")) else max(4 * noise, 1e-6)
+        assert small or (diff <= bound and diff < 5e-2), (k, diff, noise)
