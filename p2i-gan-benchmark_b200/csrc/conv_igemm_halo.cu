@@ -658,7 +658,10 @@ int run_igemm_halo(const void* x, const void* w, const P2iConvDesc& d, const voi
     }
     p.n_tiles = d.Cout / NT;
     p.SA = (budget - b_bytes) / HALO_A_STRIDE;
-    if (p.SA > 8) p.SA = 8;
+    // Ring depth cap (P2I_HALO_SA_MAX, default 8): every stage not taken is 23 KB of shared memory that a concurrent CUDA-core
+    // kernel's CTAs (bias column sums, the thin first 3-D layer, Adam ...) can use to co-reside with this kernel's CTA.
+    static const int sa_max = [] { const char* e = getenv("P2I_HALO_SA_MAX"); const int v = e ? atoi(e) : 8; return v < 2 ? 2 : (v > 8 ? 8 : v); }();
+    if (p.SA > sa_max) p.SA = sa_max;
     if (p.SA < 2 * p.MB) return 1;
     p.NACC = (p.MB * NT * 2 <= 512) ? 2 : 1;
     const int cols = p.NACC * p.MB * NT;

@@ -398,12 +398,11 @@ __global__ void idw_interp_kernel(const int* __restrict__ nbr_idx, const float* 
 }
 
 // dvals[b, idx] += w * dout (backward of the interpolation; reference: autograd through layer.py:284-291).
-// Shared-memory float atomics are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN; so are the 64-bit integer ones), so the
-// kernel issues as few of them as it can.  Lanes of a warp take 32 CONSECUTIVE queries (coalesced loads); their k-th
+// Shared-memory float atomics are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN; so are the 64-bit integer ones) and every
+// atomic is a serialisation point, so the kernel issues as few as it can.  Lanes of a warp take 32 CONSECUTIVE queries (coalesced loads); their k-th
 // neighbours form a few runs of equal point indices (the 4-neighbour set changes every few pixels), which are summed with a
 // segmented warp scan; only the last lane of a run issues an atomic (about 6x fewer than one per query and neighbour).
-// The sums are still privatised per block in shared memory (one global RED per touched point and block).
-constexpr int IDW_BWD_PTS = 8192;
+// The surviving sums go straight to global memory as fp32 REDs (native, unlike the shared-memory form).
 constexpr int IDW_BWD_ITERS = 8;                       // 32-query groups per warp: a block covers 8 * 8 * 32 = 2048 queries
 
 __device__ __forceinline__ void idw_run_add(float* dst, int id, float val, int lane) {
@@ -423,17 +422,13 @@ __device__ __forceinline__ void idw_run_add(float* dst, int id, float val, int l
 __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ nbr_idx,
                                                              const float* __restrict__ nbr_w, const int* __restrict__ counts,
                                                              const int* __restrict__ src, int cap, float* __restrict__ dvals, int Q) {
-    __shared__ float acc[IDW_BWD_PTS];
+    // No shared memory at all: this kernel sits at the tail of the backward pass next to weight-gradient CTAs that own 220 KB
+    // of an SM's shared memory -- with a 32-KB privatised accumulator its blocks could only be placed on SMs those CTAs had
+    // left (204-330 us in the step against ~90 us alone).  After the run aggregation the global REDs are few enough.
     const int b = blockIdx.y;
-    const int N = counts[b];
-    if (N == 0) return;
-    const bool priv = N <= IDW_BWD_PTS;
-    if (priv)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
+    if (counts[b] == 0) return;
     const int sb = src ? src[b] : b;
-    float* v = dvals + static_cast<size_t>(b) * cap;
-    float* dst = priv ? acc : v;
+    float* dst = dvals + static_cast<size_t>(b) * cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int4* idp = reinterpret_cast<const int4*>(nbr_idx) + static_cast<size_t>(sb) * Q;
     const float4* wp = reinterpret_cast<const float4*>(nbr_w) + static_cast<size_t>(sb) * Q;
@@ -456,11 +451,6 @@ __global__ void __launch_bounds__(256) idw_interp_bwd_kernel(const float* __rest
         idw_run_add(dst, (w.y != 0.f && g != 0.f) ? id.y : -1, w.y * g, lane);
         idw_run_add(dst, (w.z != 0.f && g != 0.f) ? id.z : -1, w.z * g, lane);
         idw_run_add(dst, (w.w != 0.f && g != 0.f) ? id.w : -1, w.w * g, lane);
-    }
-    if (priv) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < N; i += blockDim.x)
-            if (acc[i] != 0.f) atomicAdd(v + i, acc[i]);
     }
 }
 

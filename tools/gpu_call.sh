@@ -21,6 +21,7 @@ for s in $steps; do
     graph2) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/prof_graph.py gpurun_out/${tag}_graph2_timeline.txt > gpurun_out/${tag}_graph2_kernels.txt 2>&1; echo "graph2 rc=$?"; grep "^kernels" gpurun_out/${tag}_graph2_kernels.txt;;
     blocks2) for nb in 8 16 64; do P2I_PEER_BLOCKS=$nb timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2957${nb:0:1} bench.py --gpus 2 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_2gpu_blocks$nb.json 2> gpurun_out/${tag}_bench_2gpu_blocks$nb.err; echo "blocks=$nb rc=$?"; head -c 250 gpurun_out/${tag}_bench_2gpu_blocks$nb.json; echo; done;;
     bench8) for b in 1 0; do P2I_BUCKETED=$b timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2954$b bench.py --gpus 8 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_8gpu_bucketed$b.json 2> gpurun_out/${tag}_bench_8gpu_bucketed$b.err; echo "bench8 bucketed=$b rc=$?"; head -c 300 gpurun_out/${tag}_bench_8gpu_bucketed$b.json; echo; done;;
+    samax) for v in 3 4 8; do P2I_HALO_SA_MAX=$v timeout 600 python bench.py --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_samax$v.json 2> gpurun_out/${tag}_bench_samax$v.err; echo "samax=$v rc=$?"; head -c 240 gpurun_out/${tag}_bench_samax$v.json; echo; done;;
     benchq) timeout 600 python bench.py --steps 50 --no-cpu --no-extras > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err; echo "benchq rc=$?"; head -c 400 gpurun_out/${tag}_bench_quick.json;;
     others) for wl in gauge1pct stress256; do timeout 600 python bench.py --workload $wl --steps 100 --no-extras --no-cpu > gpurun_out/${tag}_bench_$wl.json 2> gpurun_out/${tag}_bench_$wl.err; echo "$wl rc=$?"; done;;
     infer) timeout 600 python bench.py --workload infer --steps 100 --no-extras > gpurun_out/${tag}_bench_infer.json 2> gpurun_out/${tag}_bench_infer.err; echo "infer rc=$?";;
