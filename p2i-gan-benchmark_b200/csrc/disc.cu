@@ -28,24 +28,26 @@ __device__ __forceinline__ float blk_sum(float v, float* sh) {   // result valid
 // scratch per layer: [0] ss1, [1] ss2, [2 .. 2+rows) t2'   (K3 leaves ss1, ss2 at zero for the next call)
 // ------------------------------------------------------------------------------------------------
 // block = 32 columns x 8 row slices (coalesced 128-B row reads, 8 independent partial sums per column)
-__global__ void __launch_bounds__(256) sn_wtu_kernel(const P2iSnLayer* __restrict__ table) {
+__global__ void __launch_bounds__(1024) sn_wtu_kernel(const P2iSnLayer* __restrict__ table) {
+    // block = 32 columns x 32 row lanes: R / 32 <= 8 loads per thread, all issued together (one DRAM round trip; with 8 row
+    // lanes the 32 dependent-latency iterations made this 20-us kernel pure long-scoreboard stall)
     const P2iSnLayer L = table[blockIdx.y];
-    __shared__ float part[8][33];
+    __shared__ float part[32][33];
     const int R = L.rows, K = L.cols;
     if (blockIdx.x * 32 >= K) return;
     const int jl = threadIdx.x & 31, rs = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + jl;
     float s = 0.f;
     if (j < K) {
-#pragma unroll 4
-        for (int i = rs; i < R; i += 8) s = fmaf(__ldg(L.W + static_cast<size_t>(i) * K + j), __ldg(L.u + i), s);
+#pragma unroll 8
+        for (int i = rs; i < R; i += 32) s = fmaf(__ldg(L.W + static_cast<size_t>(i) * K + j), __ldg(L.u + i), s);
     }
     part[rs][jl] = s;
     __syncthreads();
     if (rs == 0) {
         float t = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t += part[q][jl];
+        for (int q = 0; q < 32; ++q) t += part[q][jl];
         if (j < K) L.v[j] = t;                          // un-normalised; K3 divides by n1
         const float ss = warp_sum(j < K ? t * t : 0.f);
         if (jl == 0) atomicAdd(&L.scratch[0], ss);
@@ -464,7 +466,7 @@ extern "C" int p2i_spectral_norm(const P2iSnLayer* table_dev, int n_layers, int 
                                  void* stream) {
     P2I_CHECK_ARG(table_dev && n_layers > 0 && max_rows > 0 && max_cols > 0, "spectral_norm: bad arguments");
     if (training) {
-        sn_wtu_kernel<<<dim3(cdiv(max_cols, 32), n_layers), 256, 0, as_stream(stream)>>>(table_dev);
+        sn_wtu_kernel<<<dim3(cdiv(max_cols, 32), n_layers), 1024, 0, as_stream(stream)>>>(table_dev);
         P2I_CHECK_LAUNCH("sn_wtu_kernel");
     }
     sn_wv_kernel<<<dim3(cdiv(max_rows, 2), n_layers), 256, 0, as_stream(stream)>>>(table_dev);

@@ -582,46 +582,70 @@ __global__ void __launch_bounds__(256) disc_unpack_input_grad_kernel(const __nv_
 // Spectral-norm backward (+ un-packing of tensor-core weight gradients), one block per layer:
 //   G = dL/dW_sn (packed [tap'][Cout][Cin'] or plain [Cout][K]);  dW_orig = G/sigma - (<G, W_orig>/sigma^2) u v^T
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t packed_index(const P2iSnGrad& L, int co, int ci, int r) {
-    if (!L.packed) return (static_cast<size_t>(co) * L.Cin + ci) * (L.KT * L.ksize * L.ksize) + r;
-    const int k = L.ksize, kk = k * k;
-    const int kt = r / kk, ky = (r % kk) / k, kx = r % k;
-    if (L.s2) {
-        const int dy = ky == 0 ? 0 : 1, py = ky == 1 ? 0 : 1, dx = kx == 0 ? 0 : 1, px = kx == 1 ? 0 : 1;
-        const int tap = (kt * 2 + dy) * 2 + dx;
-        return (static_cast<size_t>(tap) * L.Cout + co) * (4 * L.Cin) + (py * 2 + px) * L.Cin + ci;
-    }
-    const int tap = (kt * k + ky) * k + kx;
-    return (static_cast<size_t>(tap) * L.Cout + co) * L.cin_pad + ci;
-}
-
 constexpr int SN_BWD_BLOCKS = 64;   // blocks per layer
-// pass 1: inner[layer] += <G, W_orig>   pass 2: dW = G/sigma - inner/sigma^2 * u v^T
-// 32-bit index arithmetic throughout (a layer has < 2^31 weights; 64-bit div/mod dominated these kernels).
-__global__ void __launch_bounds__(256) sn_bwd_inner_kernel(const P2iSnGrad* __restrict__ table, float* __restrict__ inner) {
-    const P2iSnGrad L = table[blockIdx.y];
-    __shared__ float sh[32];
+constexpr int SN_ROW_MAX = 3456;    // largest Cin * taps of a layer (d3d.6: 128 * 27)
+
+// One output-channel row of G (all Cin x taps entries of `co`) -> shared memory in weight_orig order [ci][r].  The packed
+// forms are read plane by plane, i.e. with consecutive threads on consecutive ci (coalesced), and transposed on the way
+// in; round 1 gathered G element by element in weight_orig order (one 4-byte read per tap plane per thread, two 32-bit
+// divisions and the un-packing branch per element: 148 instructions per weight, 35 us per launch).
+__device__ __forceinline__ void sn_stage_row(const P2iSnGrad& L, int co, float* __restrict__ sG) {
     const int per = L.KT * L.ksize * L.ksize;
     const int K = L.Cin * per;
-    const int total = L.Cout * K;
+    if (!L.packed) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x) sG[i] = L.G[static_cast<size_t>(co) * K + i];
+        return;
+    }
+    const int lc = __ffs(L.Cin) - 1;                       // Cin is a power of two (16 .. 256)
+    if (!L.s2) {
+        const int n = per << lc;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int tap = i >> lc, ci = i & (L.Cin - 1);
+            sG[ci * per + tap] = L.G[(static_cast<size_t>(tap) * L.Cout + co) * L.cin_pad + ci];
+        }
+        return;
+    }
+    // space-to-depth layers: plane tap' = (kt*2 + dy)*2 + dx, row = [(py*2 + px)][ci]; (dy,py) = (0,1),(1,0),(1,1) <-> ky = 0,1,2
+    const int n = (L.KT * 4 * 4) << lc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ci = i & (L.Cin - 1), q = (i >> lc) & 3, tp = i >> (lc + 2);
+        const int kt = tp >> 2, dy = (tp >> 1) & 1, dx = tp & 1, py = q >> 1, px = q & 1;
+        const int ky = dy ? (py ? 2 : 1) : (py ? 0 : -1), kx = dx ? (px ? 2 : 1) : (px ? 0 : -1);
+        if (ky < 0 || kx < 0) continue;                     // the (0,0) sub-position carries no weight
+        sG[ci * per + (kt * 3 + ky) * 3 + kx] = L.G[(static_cast<size_t>(tp) * L.Cout + co) * (4 * L.Cin) + (q << lc) + ci];
+    }
+}
+
+// pass 1: inner[layer] += <G, W_orig>   pass 2: dW = G/sigma - inner/sigma^2 * u v^T      (block = rows co, co + 64, ...)
+__global__ void __launch_bounds__(256) sn_bwd_inner_kernel(const P2iSnGrad* __restrict__ table, float* __restrict__ inner) {
+    const P2iSnGrad L = table[blockIdx.y];
+    __shared__ float sG[SN_ROW_MAX];
+    __shared__ float sh[32];
+    const int K = L.Cin * L.KT * L.ksize * L.ksize;
     float acc = 0.f;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int co = e / K, rem = e - co * K, ci = rem / per, r = rem - ci * per;
-        acc = fmaf(L.G[packed_index(L, co, ci, r)], L.W[e], acc);
+    for (int co = blockIdx.x; co < L.Cout; co += gridDim.x) {
+        sn_stage_row(L, co, sG);
+        __syncthreads();
+        const float* w = L.W + static_cast<size_t>(co) * K;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) acc = fmaf(sG[i], w[i], acc);
+        __syncthreads();
     }
     acc = blk_sum_all(acc, sh);
     if (threadIdx.x == 0 && acc != 0.f) atomicAdd(&inner[blockIdx.y], acc);
 }
 __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const P2iSnGrad* __restrict__ table, const float* __restrict__ inner) {
     const P2iSnGrad L = table[blockIdx.y];
-    const int per = L.KT * L.ksize * L.ksize;
-    const int K = L.Cin * per;
-    const int total = L.Cout * K;
+    __shared__ float sG[SN_ROW_MAX];
+    const int K = L.Cin * L.KT * L.ksize * L.ksize;
     const float sig = *L.sigma;
     const float c1 = 1.f / sig, c2 = inner[blockIdx.y] / (sig * sig);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int co = e / K, rem = e - co * K, ci = rem / per, r = rem - ci * per;
-        L.dW[e] += L.G[packed_index(L, co, ci, r)] * c1 - c2 * L.u[co] * L.v[rem];
+    for (int co = blockIdx.x; co < L.Cout; co += gridDim.x) {
+        sn_stage_row(L, co, sG);
+        __syncthreads();
+        float* dw = L.dW + static_cast<size_t>(co) * K;
+        const float cu = c2 * L.u[co];
+        for (int i = threadIdx.x; i < K; i += blockDim.x) dw[i] += sG[i] * c1 - cu * L.v[i];
+        __syncthreads();
     }
 }
 
@@ -720,6 +744,8 @@ extern "C" int p2i_disc_unpack_input_grad(const void* g, float* dx, int B, int C
 
 extern "C" int p2i_spectral_norm_bwd(const P2iSnGrad* table_dev, int n_layers, float* inner_scratch, void* stream) {
     P2I_CHECK_ARG(table_dev && n_layers > 0 && inner_scratch, "spectral_norm_bwd: bad arguments");
+    // (layers are the discriminator's: Cin a power of two, Cin * taps <= SN_ROW_MAX; the table lives on the device, so this is
+    //  the caller's contract -- disc_bwd.py builds it from the module's own shapes)
     dim3 grid(SN_BWD_BLOCKS, n_layers);
     sn_bwd_inner_kernel<<<grid, 256, 0, as_stream(stream)>>>(table_dev, inner_scratch);
     P2I_CHECK_LAUNCH("sn_bwd_inner_kernel");

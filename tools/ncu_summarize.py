@@ -16,6 +16,30 @@ KEYS = [
 ]
 
 
+GLUE_KEYS = [
+    ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"), ("gpu__time_duration.sum", "us"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts%"),
+    ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "st_lg"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "st_mio"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_bar"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
+    ("smsp__inst_executed.sum", "inst"),
+]
+if "--glue" in sys.argv:
+    sys.argv.remove("--glue")
+    KEYS = GLUE_KEYS
+
+
 def to_bytes(v, unit):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
