@@ -809,7 +809,9 @@ def run_ours(args):
     set_stream_overlap(False)
     kt = timed_pass(ConvTimer(True)).result()
     hbm_kernels = None
-    if rank == 0 and not args.no_extras:
+    if not args.no_extras:
+        # EVERY rank runs this pass (its steps contain the gradient exchanges: a rank that skipped them would leave its peers
+        # spinning in the exchange kernel until the time-out); rank 0 reports
         sustained_pk, burst_pk, hbm_pk, src_pk = peaks()
         try:
             hbm_kernels = timed_pass(GlueTimer(_model_bytes(w.G, w.D, w.ts))).result(psteps, hbm_pk)

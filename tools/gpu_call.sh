@@ -20,15 +20,10 @@ for s in $steps; do
     bench2) for b in 1 0; do P2I_BUCKETED=$b timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2953$b bench.py --gpus 2 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_2gpu_bucketed$b.json 2> gpurun_out/${tag}_bench_2gpu_bucketed$b.err; echo "bench2 bucketed=$b rc=$?"; head -c 300 gpurun_out/${tag}_bench_2gpu_bucketed$b.json; echo; done;;
     graph2) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/prof_graph.py gpurun_out/${tag}_graph2_timeline.txt > gpurun_out/${tag}_graph2_kernels.txt 2>&1; echo "graph2 rc=$?"; grep "^kernels" gpurun_out/${tag}_graph2_kernels.txt;;
     blocks2) for nb in 8 16 64; do P2I_PEER_BLOCKS=$nb timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2957${nb:0:1} bench.py --gpus 2 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_2gpu_blocks$nb.json 2> gpurun_out/${tag}_bench_2gpu_blocks$nb.err; echo "blocks=$nb rc=$?"; head -c 250 gpurun_out/${tag}_bench_2gpu_blocks$nb.json; echo; done;;
-    bench8) for b in 1 0; do P2I_BUCKETED=$b timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2954$b bench.py --gpus 8 --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_8gpu_bucketed$b.json 2> gpurun_out/${tag}_bench_8gpu_bucketed$b.err; echo "bench8 bucketed=$b rc=$?"; head -c 300 gpurun_out/${tag}_bench_8gpu_bucketed$b.json; echo; done;;
-    ncuglue)
-      timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err &&
-      timeout 900 ncu --set full --clock-control none -k regex:"upmod_bwd|sn_bwd|d3d_first|stem_bwd|sn_wtu|sn_wv|sn_finish|disc_pack|colsum|doconv_bwd|d2d_last|tail_bwd|head_bwd|pyramid_bwd|idw_interp_bwd|gate_points_bwd|upmod_fwd|stem_fwd|adam_kernel|rec_loss|doconv_compose" -s 330 -c 75 -o gpurun_out/${tag}_glue_full \
-          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_glue.log 2>&1
-      echo "ncu glue rc=$?"
-      ncu -i gpurun_out/${tag}_glue_full.ncu-rep --page raw --csv > /tmp/glue_raw.csv 2>/dev/null && python tools/ncu_summarize.py --glue /tmp/glue_raw.csv gpurun_out/${tag}_glue_full_summary.txt
-      mv gpurun_out/${tag}_glue_full.ncu-rep /tmp/ 2>/dev/null; du -sh gpurun_out;;
-    samax) for v in 3 4 8; do P2I_HALO_SA_MAX=$v timeout 600 python bench.py --steps 100 --no-cpu --no-extras > gpurun_out/${tag}_bench_samax$v.json 2> gpurun_out/${tag}_bench_samax$v.err; echo "samax=$v rc=$?"; head -c 240 gpurun_out/${tag}_bench_samax$v.json; echo; done;;
+    bench8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 8 --steps 400 --warmup 5 > gpurun_out/${tag}_bench_train_8gpu.json 2> gpurun_out/${tag}_bench_train_8gpu.err; echo "bench8 train rc=$?"; head -c 300 gpurun_out/${tag}_bench_train_8gpu.json; echo
+            timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --workload infer --steps 400 --warmup 5 > gpurun_out/${tag}_bench_infer_8gpu.json 2> gpurun_out/${tag}_bench_infer_8gpu.err; echo "bench8 infer rc=$?"; head -c 300 gpurun_out/${tag}_bench_infer_8gpu.json; echo
+            P2I_BUCKETED=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 100 --warmup 5 --no-extras --no-cpu > gpurun_out/${tag}_bench_train_8gpu_bucketed.json 2> gpurun_out/${tag}_bench_train_8gpu_bucketed.err; echo "bench8 bucketed rc=$?"; head -c 300 gpurun_out/${tag}_bench_train_8gpu_bucketed.json; echo;;
+    bench4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 4 --steps 400 --warmup 5 > gpurun_out/${tag}_bench_train_4gpu.json 2> gpurun_out/${tag}_bench_train_4gpu.err; echo "bench4 train rc=$?"; head -c 300 gpurun_out/${tag}_bench_train_4gpu.json; echo;;
     benchq) timeout 600 python bench.py --steps 50 --no-cpu --no-extras > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err; echo "benchq rc=$?"; head -c 400 gpurun_out/${tag}_bench_quick.json;;
     others) for wl in gauge1pct stress256; do timeout 600 python bench.py --workload $wl --steps 100 --no-extras --no-cpu > gpurun_out/${tag}_bench_$wl.json 2> gpurun_out/${tag}_bench_$wl.err; echo "$wl rc=$?"; done;;
     infer) timeout 600 python bench.py --workload infer --steps 100 --no-extras > gpurun_out/${tag}_bench_infer.json 2> gpurun_out/${tag}_bench_infer.err; echo "infer rc=$?";;
