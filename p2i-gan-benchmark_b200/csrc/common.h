@@ -47,4 +47,10 @@ void set_last_variant(int code);
 // Programmatic dependent launch of the tensor-core kernels (p2i_set_pdl; default off, P2I_PDL=1 in the environment turns it on).
 bool pdl_enabled();
 
+// d3d_first_mma.cu: tensor-core (mma.sync) forward / weight gradient of the one-input-channel Conv3d d3d.0
+bool d3d_first_mma_ok(int T, int H, int W);
+int d3d_first_fwd_mma(const float* x, const float* w, const float* sigma, const float* bias, void* y, int B, int T, int H, int W,
+                      cudaStream_t stream);
+int d3d_first_bwd_w_mma(const void* dpre, const float* x, float* dW, float* db, int B, int T, int H, int W, cudaStream_t stream);
+
 }  // namespace p2i

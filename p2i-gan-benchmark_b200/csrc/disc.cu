@@ -499,6 +499,7 @@ extern "C" int p2i_d3d_first_fwd(const float* x, const float* w, const float* si
     P2I_CHECK_ARG(H % 4 == 0 && W % 4 == 0, "d3d_first_fwd: H, W must be multiples of 4");
     P2I_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 31), "d3d_first_fwd: tensor too large for 32-bit indexing");
     const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
+    if (d3d_first_mma_ok(T, H, W)) return d3d_first_fwd_mma(x, w, sigma, bias, y, B, T, H, W, as_stream(stream));
     if (W % 8 == 0) {
         d3d_first_fwd4_kernel<<<static_cast<unsigned>((total / 4 + 31) / 32), 128, 0, as_stream(stream)>>>(
             x, w, sigma, bias, static_cast<__nv_bfloat16*>(y), B, T, H, W);

@@ -704,7 +704,10 @@ extern "C" int p2i_d3d_first_bwd(const void* dpre, const float* x, const float* 
     P2I_CHECK_ARG(static_cast<long long>(B) * T * H * W < (1ll << 31), "d3d_first_bwd: tensor too large for 32-bit indexing");
     if (dW && db) {
         const long long total = static_cast<long long>(B) * T * (H / 2) * (W / 2);
-        if (W % 8 == 0) {
+        if (d3d_first_mma_ok(T, H, W)) {
+            const int rc = d3d_first_bwd_w_mma(dpre, x, dW, db, B, T, H, W, as_stream(stream));
+            if (rc) return rc;
+        } else if (W % 8 == 0) {
             long long blocks = (total / 4 + 15) / 16;
             if (blocks > sm_count() * 2) blocks = sm_count() * 2;
             d3d_first_bwd_w4_kernel<<<static_cast<unsigned>(blocks), 192, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(dpre), x,

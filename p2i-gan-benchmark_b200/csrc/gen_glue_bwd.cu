@@ -93,74 +93,98 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 //   dbias[c] += sum dpre ;  dpos[Y,X] = s*(1 - s/2) * sum_{b,c} dpre * up(z)
 // one thread per (pixel, 8 channels); a pixel's C/8 threads are consecutive.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ pos,
+// Round 2: one thread per (pixel, 32 channels) instead of (pixel, 8 channels) -- the bilinear geometry, sigmoid(pos) and the index
+// arithmetic of a pixel are computed once per 32 channels (ncu on the 8-channel form: 47-66 % issue-slot utilisation at 35-43 %
+// occupancy, i.e. instruction-issue bound; 212 instructions per 8 channels, ~130 of them per-pixel overhead).
+__global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ pos,
                                                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ dout,
                                                            __nv_bfloat16* __restrict__ gout, float* __restrict__ dbias,
                                                            float* __restrict__ dpos, int B, int h, int w, int C) {
     extern __shared__ float s_db[];   // [C]
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
     __syncthreads();
-    const int cg = C >> 3;
-    const int total = B * 4 * h * w * cg;                      // < 2^31 (checked on the host): 32-bit index arithmetic
+    const int cg = C >> 3;                                      // 16-byte channel groups per pixel
+    const int cq = C >> 5;                                      // 32-channel quads per pixel (power of two: 2, 4, 8, 16)
+    const int total = B * 4 * h * w * cq;                       // < 2^31 (checked on the host): 32-bit index arithmetic
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
-    float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int c8 = idx & (cg - 1);                         // cg is a power of two (checked on the host)
-        const int pix = idx / cg;
-        const int r_ = pix / W2, X = pix - r_ * W2, b = r_ / H2, Y = r_ - b * H2;
+    float dbv[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dbv[a][k] = 0.f;
+    // the trip count is warp-uniform (the ds reduction below shuffles with a full mask); lanes past the end carry ds = 0
+    for (int idx0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); idx0 < total; idx0 += gridDim.x * blockDim.x) {
+        const int idx = idx0 + (threadIdx.x & 31);
+        const bool valid = idx < total;
+        float ds = 0.f, s = 0.f;
+        int Y = 0, X = 0;
+        if (valid) {
+        const int q4 = idx & (cq - 1);
+        const int pix = idx / cq;
+        const int r_ = pix / W2, b = r_ / H2;
+        X = pix - r_ * W2;
+        Y = r_ - b * H2;
         const float fy = sy * Y, fx = sx * X;
         const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
         const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
         const float ly = fy - y0, lx = fx - x0;
         const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-        const float s = 2.f / (1.f + __expf(-pos[static_cast<size_t>(Y) * W2 + X]));
-        const uint4* zb = reinterpret_cast<const uint4*>(z + static_cast<size_t>(b) * h * w * C) + c8;
-        const uint4 a = __ldg(zb + (static_cast<size_t>(y0) * w + x0) * cg), bq = __ldg(zb + (static_cast<size_t>(y0) * w + x1) * cg);
-        const uint4 c = __ldg(zb + (static_cast<size_t>(y1) * w + x0) * cg), d = __ldg(zb + (static_cast<size_t>(y1) * w + x1) * cg);
-        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
-        const uint32_t cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
-        const size_t o = static_cast<size_t>(pix) * cg + c8;
-        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(dout) + o);
-        const uint32_t gv[4] = {gq.x, gq.y, gq.z, gq.w};
-        const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2);
-        const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias) + c8 * 2 + 1);
-        const float bb[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
-        uint32_t ov[4];
-        float ds = 0.f;
+        s = 2.f / (1.f + __expf(-pos[static_cast<size_t>(Y) * W2 + X]));
+        const uint4* zb = reinterpret_cast<const uint4*>(z + static_cast<size_t>(b) * h * w * C) + q4 * 4;
+        const uint4* za = zb + (static_cast<size_t>(y0) * w + x0) * cg;
+        const uint4* zbq = zb + (static_cast<size_t>(y0) * w + x1) * cg;
+        const uint4* zc = zb + (static_cast<size_t>(y1) * w + x0) * cg;
+        const uint4* zd = zb + (static_cast<size_t>(y1) * w + x1) * cg;
+        const size_t o = static_cast<size_t>(pix) * cg + q4 * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 fa = unpack_bf16x2(av[i]), fb = unpack_bf16x2(bv[i]), fc = unpack_bf16x2(cv[i]), fd = unpack_bf16x2(dv[i]);
-            const float2 gg = unpack_bf16x2(gv[i]);
-            const float u0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
-            const float u1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
-            const float d0 = (fmaf(s, u0, bb[2 * i]) > 0.f) ? gg.x : 0.f;
-            const float d1 = (fmaf(s, u1, bb[2 * i + 1]) > 0.f) ? gg.y : 0.f;
-            ds += d0 * u0 + d1 * u1;
-            dbv[2 * i] += d0;          // the thread keeps its channel group for the whole loop (stride % cg == 0)
-            dbv[2 * i + 1] += d1;
-            ov[i] = pack_bf16x2(s * d0, s * d1);
+        for (int a4 = 0; a4 < 4; ++a4) {
+            const uint4 a = __ldg(za + a4), bq = __ldg(zbq + a4), c = __ldg(zc + a4), d = __ldg(zd + a4);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+            const uint32_t cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            const uint4 gq = __ldg(reinterpret_cast<const uint4*>(dout) + o + a4);
+            const uint32_t gv[4] = {gq.x, gq.y, gq.z, gq.w};
+            const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * 4 + a4) * 2);
+            const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * 4 + a4) * 2 + 1);
+            const float bb[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
+            uint32_t ov[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = unpack_bf16x2(av[i]), fb = unpack_bf16x2(bv[i]), fc = unpack_bf16x2(cv[i]), fd = unpack_bf16x2(dv[i]);
+                const float2 gg = unpack_bf16x2(gv[i]);
+                const float u0 = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+                const float u1 = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+                const float d0 = (fmaf(s, u0, bb[2 * i]) > 0.f) ? gg.x : 0.f;
+                const float d1 = (fmaf(s, u1, bb[2 * i + 1]) > 0.f) ? gg.y : 0.f;
+                ds += d0 * u0 + d1 * u1;
+                dbv[a4][2 * i] += d0;  // the thread keeps its channel quad for the whole loop (stride % cq == 0)
+                dbv[a4][2 * i + 1] += d1;
+                ov[i] = pack_bf16x2(s * d0, s * d1);
+            }
+            reinterpret_cast<uint4*>(gout)[o + a4] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
         }
-        reinterpret_cast<uint4*>(gout)[o] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        // reduce ds over the pixel's cg consecutive threads (cg is a power of two >= 8; groups never straddle a warp
-        // when cg <= 32, otherwise every warp holds a single pixel)
-        const int span = cg < 32 ? cg : 32;
-        for (int off = span >> 1; off > 0; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
-        if ((threadIdx.x & (span - 1)) == 0 && ds != 0.f)
+        }
+        // reduce ds over the pixel's cq consecutive threads (cq is a power of two <= 32: groups never straddle a warp)
+        for (int off = cq >> 1; off > 0; off >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, off);
+        if (valid && (threadIdx.x & (cq - 1)) == 0 && ds != 0.f)
             atomicAdd(&dpos[static_cast<size_t>(Y) * W2 + X], ds * s * (1.f - 0.5f * s));
     }
-    // bias gradient: registers -> (lanes sharing a channel group folded by shuffles when cg < 32) -> shared -> global
+    // bias gradient: registers -> lanes sharing a channel quad folded by shuffles -> shared -> global
     {
-        const int c8 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) & (cg - 1));
-        for (int off = 16; off >= cg; off >>= 1) {
+        const int q4 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) & (cq - 1));
+        for (int off = 16; off >= cq; off >>= 1) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dbv[k] += __shfl_xor_sync(0xffffffffu, dbv[k], off);
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dbv[a][k] += __shfl_xor_sync(0xffffffffu, dbv[a][k], off);
         }
-        if (cg >= 32 || (threadIdx.x & 31) < cg) {
+        if ((threadIdx.x & 31) < cq) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (dbv[k] != 0.f) atomicAdd(&s_db[c8 * 8 + k], dbv[k]);
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (dbv[a][k] != 0.f) atomicAdd(&s_db[(q4 * 4 + a) * 8 + k], dbv[a][k]);
         }
     }
     __syncthreads();
@@ -168,53 +192,90 @@ __global__ void __launch_bounds__(256) upmod_bwd_hi_kernel(const __nv_bfloat16* 
         if (s_db[i] != 0.f) atomicAdd(&dbias[i], s_db[i]);
 }
 
-// pass 2 (low resolution): dz = transpose(bilinear x2, align_corners) applied to g.  Gather form: every
-// low-res pixel visits the (at most 5x5) high-res pixels whose interpolation footprint contains it.
-__global__ void __launch_bounds__(256) upmod_bwd_lo_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dz,
+// pass 2 (low resolution): dz = transpose(bilinear x2, align_corners) applied to g.  Gather form: every low-res pixel visits
+// the high-res pixels whose interpolation footprint contains it.  One thread per (pixel, 32 channels); the horizontal weights of
+// the (at most 10) candidate columns are computed once per thread, the vertical weight once per candidate row.
+__global__ void __launch_bounds__(256, 2) upmod_bwd_lo_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dz,
                                                            int B, int h, int w, int C) {
-    const int cg = C >> 3;
-    const int total = B * h * w * cg;                          // < 2^31 (checked on the host)
+    const int cg = C >> 3, cq = C >> 5;
+    const int total = B * h * w * cq;                          // < 2^31 (checked on the host)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int pix = idx / cg, c8 = idx - pix * cg;
+    const int pix = idx / cq, q4 = idx - pix * cq;
     const int r_ = pix / w, x = pix - r_ * w, b = r_ / h, y = r_ - b * h;
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
-    // candidate high-res rows: those with floor(sy*Y) in {y-1, y}
+    // candidate high-res rows / columns: those with floor(s*Y) in {y-1, y}  (a window of at most 7 for a x2 upsample)
     int Ya = (sy > 0.f) ? static_cast<int>(floorf((y - 1) / sy)) - 1 : 0, Yb = (sy > 0.f) ? static_cast<int>(ceilf((y + 1) / sy)) + 1 : H2 - 1;
     int Xa = (sx > 0.f) ? static_cast<int>(floorf((x - 1) / sx)) - 1 : 0, Xb = (sx > 0.f) ? static_cast<int>(ceilf((x + 1) / sx)) + 1 : W2 - 1;
     Ya = Ya < 0 ? 0 : Ya; Xa = Xa < 0 ? 0 : Xa;
     Yb = Yb > H2 - 1 ? H2 - 1 : Yb; Xb = Xb > W2 - 1 ? W2 - 1 : Xb;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint4* gb = reinterpret_cast<const uint4*>(g + static_cast<size_t>(b) * H2 * W2 * C) + c8;
-    for (int Y = Ya; Y <= Yb; ++Y) {
-        const float fy = sy * Y;
-        const int y0 = static_cast<int>(fy);
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-        const float ly = fy - y0;
-        const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
-        if (wy == 0.f) continue;
-        for (int X = Xa; X <= Xb; ++X) {
-            const float fx = sx * X;
-            const int x0 = static_cast<int>(fx);
-            const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
-            const float lx = fx - x0;
-            const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-            if (wx == 0.f) continue;
-            const float wt = wy * wx;
-            const uint4 q = __ldg(gb + (static_cast<size_t>(Y) * W2 + X) * cg);
-            const uint32_t qv[4] = {q.x, q.y, q.z, q.w};
+    auto weight = [](int P, float sc, int n, int p) -> float {       // weight of low-res index p in high-res index P
+        const float f = sc * P;
+        const int p0 = static_cast<int>(f);
+        const int p1 = p0 + (p0 < n - 1 ? 1 : 0);
+        const float l = f - p0;
+        return (p0 == p ? 1.f - l : 0.f) + (p1 == p ? l : 0.f);
+    };
+    float acc[4][8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(qv[i]);
-                acc[2 * i] = fmaf(wt, f.x, acc[2 * i]);
-                acc[2 * i + 1] = fmaf(wt, f.y, acc[2 * i + 1]);
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    const uint4* gb = reinterpret_cast<const uint4*>(g + static_cast<size_t>(b) * H2 * W2 * C) + q4 * 4;
+    if (Xb - Xa < 10) {                                        // always, for w >= 2: the window is 4 + 2 / (w - 1) wide plus margins
+        float wx[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) wx[k] = (Xa + k <= Xb) ? weight(Xa + k, sx, w, x) : 0.f;
+        for (int Y = Ya; Y <= Yb; ++Y) {
+            const float wy = weight(Y, sy, h, y);
+            if (wy == 0.f) continue;
+            const uint4* row = gb + (static_cast<size_t>(Y) * W2 + Xa) * cg;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                if (wx[k] == 0.f) continue;
+                const float wt = wy * wx[k];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const uint4 q = __ldg(row + static_cast<size_t>(k) * cg + a);
+                    const uint32_t qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack_bf16x2(qv[i]);
+                        acc[a][2 * i] = fmaf(wt, f.x, acc[a][2 * i]);
+                        acc[a][2 * i + 1] = fmaf(wt, f.y, acc[a][2 * i + 1]);
+                    }
+                }
+            }
+        }
+    } else {                                                   // degenerate geometry (w == 1): every column is a candidate
+        for (int Y = Ya; Y <= Yb; ++Y) {
+            const float wy = weight(Y, sy, h, y);
+            if (wy == 0.f) continue;
+            for (int X = Xa; X <= Xb; ++X) {
+                const float wxv = weight(X, sx, w, x);
+                if (wxv == 0.f) continue;
+                const float wt = wy * wxv;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const uint4 q = __ldg(gb + (static_cast<size_t>(Y) * W2 + X) * cg + a);
+                    const uint32_t qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack_bf16x2(qv[i]);
+                        acc[a][2 * i] = fmaf(wt, f.x, acc[a][2 * i]);
+                        acc[a][2 * i + 1] = fmaf(wt, f.y, acc[a][2 * i + 1]);
+                    }
+                }
             }
         }
     }
-    reinterpret_cast<uint4*>(dz)[static_cast<size_t>(pix) * cg + c8] =
-        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        reinterpret_cast<uint4*>(dz)[static_cast<size_t>(pix) * cg + q4 * 4 + a] =
+            make_uint4(pack_bf16x2(acc[a][0], acc[a][1]), pack_bf16x2(acc[a][2], acc[a][3]), pack_bf16x2(acc[a][4], acc[a][5]),
+                       pack_bf16x2(acc[a][6], acc[a][7]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -533,16 +594,17 @@ extern "C" int p2i_head_bwd(const float* dout, const float* out, const void* x, 
 extern "C" int p2i_upmod_bwd(const void* z, const float* pos, const float* bias, const void* dout, void* g_scratch, void* dz,
                              float* dbias, float* dpos, int B, int h, int w, int C, void* stream) {
     P2I_CHECK_ARG(z && pos && bias && dout && g_scratch && dz && dbias && dpos, "upmod_bwd: null pointer");
-    P2I_CHECK_ARG(C % 64 == 0 && (C & (C - 1)) == 0, "upmod_bwd: C=%d must be a power of two >= 64", C);
-    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
-    P2I_CHECK_ARG(total < (1ll << 31), "upmod_bwd: tensor too large for 32-bit indexing");
+    P2I_CHECK_ARG(C % 64 == 0 && (C & (C - 1)) == 0 && C <= 1024, "upmod_bwd: C=%d must be a power of two in [64, 1024]", C);
+    P2I_CHECK_ARG(static_cast<long long>(B) * 4 * h * w * (C / 8) < (1ll << 31), "upmod_bwd: tensor too large for 32-bit indexing");
+    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 32);     // one thread per (pixel, 32 channels)
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    // the grid-stride of upmod_bwd_hi must keep a thread on its channel quad: blocks * 256 is a multiple of C / 32 (a power of two <= 16)
     upmod_bwd_hi_kernel<<<static_cast<unsigned>(blocks), 256, C * sizeof(float), as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(z), pos, bias, static_cast<const __nv_bfloat16*>(dout),
         static_cast<__nv_bfloat16*>(g_scratch), dbias, dpos, B, h, w, C);
     P2I_CHECK_LAUNCH("upmod_bwd_hi_kernel");
-    const long long tl = static_cast<long long>(B) * h * w * (C / 8);
+    const long long tl = static_cast<long long>(B) * h * w * (C / 32);
     upmod_bwd_lo_kernel<<<static_cast<unsigned>((tl + 255) / 256), 256, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(g_scratch), static_cast<__nv_bfloat16*>(dz), B, h, w, C);
     P2I_CHECK_LAUNCH("upmod_bwd_lo_kernel");

@@ -160,3 +160,39 @@ def test_forward_pair_equals_two_calls():
         # so ONE sequential pair is a weak yardstick): fixed bound 1e-3 -- a race (a stale tile, a missing dependency) shows as O(0.1)
         bound = max(20 * noise, 1e-3) if k in ("lf", "lr") or k.endswith(("weight_u", "weight_v")) else max(4 * noise, 1e-6)
         assert small or (diff <= bound and diff < 5e-2), (k, diff, noise)
+
+
+@pytest.mark.parametrize("B,T,H,W", [(16, 16, 128, 128), (2, 16, 64, 64), (1, 3, 8, 32), (3, 5, 12, 96), (2, 16, 32, 40), (1, 16, 256, 256)])
+def test_d3d_first_layer_forward_and_weight_gradient(B, T, H, W):
+    """d3d.0 (Conv3d 1 -> 32, stride (1,2,2); p2igan.py:139-142) alone, through the C ABI: forward (+bias, LeakyReLU, space-to-depth
+    output layout) and dW / db / dx against torch.  W % 32 == 0 takes the warp-level tensor-core kernels (d3d_first_mma.cu; the
+    benchmark shapes), (32, 40) the CUDA-core ones.  bf16 operands, fp32 accumulation: rel-L2 <= 5e-3."""
+    import torch.nn.functional as F
+    from p2igan_b200._lib import LIB, ptr, stream
+    g = torch.Generator().manual_seed(B * 100 + T * 10 + W)
+    x = torch.randn(B, T, H, W, generator=g).to(DEV)
+    w = (torch.randn(32, 1, 3, 3, 3, generator=g) * 0.3).to(DEV).requires_grad_(True)
+    bias = (torch.randn(32, generator=g) * 0.2).to(DEV).requires_grad_(True)
+    sigma = torch.tensor([1.7], device=DEV)
+    Ho, Wo = H // 2, W // 2
+    xr = x.clone().requires_grad_(True)
+    pre = F.conv3d(xr[:, None], w / sigma, bias, stride=(1, 2, 2), padding=1)            # [B, 32, T, Ho, Wo]
+    ref = F.leaky_relu(pre, 0.2)
+    y = torch.empty(B, T, Ho // 2, Wo // 2, 128, dtype=torch.bfloat16, device=DEV)
+    LIB.call("p2i_d3d_first_fwd", ptr(x), ptr(w.detach().contiguous()), ptr(sigma), ptr(bias.detach()), ptr(y), B, T, H, W, stream())
+    got = y.float().reshape(B, T, Ho // 2, Wo // 2, 2, 2, 32).permute(0, 6, 1, 2, 4, 3, 5).reshape(B, 32, T, Ho, Wo)
+    assert rel_l2(got, ref.detach()) < 5e-3
+    # backward: dpre in the natural [B, T, Ho, Wo, 32] layout; dW is the gradient of the NORMALISED weight (w / sigma)
+    dpre = torch.randn(B, 32, T, Ho, Wo, generator=g).bfloat16().float().to(DEV)
+    wn = (w.detach() / sigma).requires_grad_(True)
+    pre2 = F.conv3d(xr[:, None], wn, bias, stride=(1, 2, 2), padding=1)
+    pre2.backward(dpre)
+    dW = torch.zeros(32, 27, device=DEV)
+    db = torch.zeros(32, device=DEV)
+    dx = torch.empty(B, T, H, W, device=DEV)
+    LIB.call("p2i_d3d_first_bwd", ptr(dpre.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)), ptr(x), ptr(w.detach().contiguous()),
+             ptr(sigma), ptr(dW), ptr(db), ptr(dx), B, T, H, W, stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dW, wn.grad.reshape(32, 27)) < 5e-3
+    assert rel_l2(db, bias.grad) < 1e-3
+    assert rel_l2(dx, xr.grad) < 5e-3

@@ -179,6 +179,34 @@ def test_generator_gradients_match_oracle_autograd(H, W, B, n_obs):
     assert not bad, bad[:8]
 
 
+@pytest.mark.parametrize("B,h,w,C", [(16, 64, 64, 64), (16, 32, 32, 128), (16, 16, 16, 256), (2, 5, 7, 64), (1, 1, 9, 128),
+                                     (3, 6, 1, 64), (1, 1, 1, 512)])
+def test_uppos_tail_backward_matches_autograd(B, h, w, C):
+    """UPPos tail (p2igan.py:60-77: x2 bilinear upsample with align_corners, 2*sigmoid(pos) gate, bias, ReLU) -- the two backward
+    kernels (one thread per pixel x 32 channels) against torch autograd on the same bf16-rounded operands; includes the three
+    shapes of the benchmark step and degenerate one-row / one-column / one-pixel maps."""
+    from p2igan_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + h * 10 + C)
+    z = torch.randn(B, C, h, w, generator=g).bfloat16().float()
+    pos = torch.randn(2 * h, 2 * w, generator=g)
+    bias = torch.randn(C, generator=g) * 0.3
+    dout = torch.randn(B, C, 2 * h, 2 * w, generator=g).bfloat16().float()
+    zr, pr, br = (t.clone().to(DEV).requires_grad_(True) for t in (z, pos, bias))
+    up = F.interpolate(zr, scale_factor=2, mode="bilinear", align_corners=True)
+    out = F.relu(2.0 * torch.sigmoid(pr)[None, None] * up + br[None, :, None, None])
+    out.backward(dout.to(DEV))
+    dbias = torch.zeros(C, device=DEV)
+    dpos = torch.zeros(2 * h, 2 * w, device=DEV)
+    dz = ops.upmod_bwd(_cl(z), pos.to(DEV), bias.to(DEV), _cl(dout), dbias, dpos)
+    torch.cuda.synchronize()
+    # the forward of the same operands first (a ReLU mask that disagreed would show up in every gradient)
+    fwd = ops.upmod_fwd(_cl(z), pos.to(DEV), bias.to(DEV))
+    assert rel_l2(fwd.float().permute(0, 3, 1, 2), out.detach()) < 5e-3
+    assert rel_l2(dz.float().permute(0, 3, 1, 2), zr.grad) < 6e-3          # bf16 scratch (s * dpre) + bf16 result
+    assert rel_l2(dbias, br.grad) < 1e-4
+    assert rel_l2(dpos, pr.grad) < 1e-3
+
+
 def test_fused_adam_matches_torch_adam():
     from p2igan_b200.optim import FusedAdam
     g = torch.Generator().manual_seed(1)

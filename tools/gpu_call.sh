@@ -7,7 +7,15 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
 for s in $steps; do
   case $s in
-    tests) timeout 1500 python -m pytest tests -m gpu -q -rf -p no:cacheprovider > gpurun_out/${tag}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.txt; tail -5 gpurun_out/${tag}_pytest.txt;;
+    guard) # a changed kernel is validated first; when its parity tests fail the remaining steps run on the previous build of the library
+      timeout 300 python -m pytest tests -m gpu -q -rf -p no:cacheprovider --timeout 90 --timeout-method=thread -k "$P2I_GUARDSEL" > gpurun_out/${tag}_pytest_guard.txt 2>&1; grc=$?
+      echo "guard rc=$grc" >> gpurun_out/${tag}_pytest_guard.txt; tail -8 gpurun_out/${tag}_pytest_guard.txt
+      if [ $grc -ne 0 ]; then export P2I_LIB_PATH=$PWD/p2i-gan-benchmark_b200/p2igan_b200/libp2i_sm100a_prev.so; echo "GUARD FAILED: using $P2I_LIB_PATH"; fi;;
+    guardb) # second changed kernel family, with a run-time switch back to the previous kernels
+      timeout 300 python -m pytest tests -m gpu -q -rf -p no:cacheprovider --timeout 90 --timeout-method=thread -k "$P2I_GUARDSEL_B" > gpurun_out/${tag}_pytest_guardb.txt 2>&1; grc=$?
+      echo "guardb rc=$grc" >> gpurun_out/${tag}_pytest_guardb.txt; tail -8 gpurun_out/${tag}_pytest_guardb.txt
+      if [ $grc -ne 0 ]; then export P2I_D3D_MMA=0; echo "GUARD B FAILED: P2I_D3D_MMA=0"; fi;;
+    tests) timeout 600 python -m pytest tests -m gpu -q -rf -p no:cacheprovider --timeout 120 --timeout-method=thread > gpurun_out/${tag}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.txt; tail -5 gpurun_out/${tag}_pytest.txt;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.txt; tail -3 gpurun_out/${tag}_smoke.txt;;
     bench) timeout 900 python bench.py > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "bench rc=$?"; head -c 600 gpurun_out/${tag}_bench_train.json;;
     bench20) timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_train20.json 2> gpurun_out/${tag}_bench_train20.err; echo "bench20 rc=$?"; head -c 600 gpurun_out/${tag}_bench_train20.json;;
@@ -33,6 +41,10 @@ for s in $steps; do
     graph) timeout 300 python tools/prof_graph.py gpurun_out/${tag}_graph_timeline.txt > gpurun_out/${tag}_graph_kernels.txt 2>&1; echo "graph rc=$?"; head -3 gpurun_out/${tag}_graph_kernels.txt;;
     convab) timeout 600 python tools/bench_conv.py > gpurun_out/${tag}_conv_ab.txt 2>&1; echo "convab rc=$?";;
     wgradab) timeout 600 python tools/bench_wgrad.py > gpurun_out/${tag}_wgrad_ab.txt 2>&1; echo "wgradab rc=$?";;
+    ncul)
+      timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_list.log 2>&1
+      echo "ncu list rc=$?";;
     ncu)
       timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err &&
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
