@@ -55,14 +55,28 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ x, unsigned
                                            int WP) {
     const int W4 = W >> 2;
     const int nvec = (T + 2) * 3 * W4;
-    for (int i = threadIdx.x; i < nvec; i += D3_THREADS) {
-        const int c4 = i % W4, fr = i / W4, f = fr / 3, r = fr - f * 3;
-        const int ti = f - 1, yi = 2 * yo + r - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ti >= 0 && ti < T && yi >= 0 && yi < H)
-            v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * T + ti) * H + yi) * W) + c4);
-        unsigned short* d = xs + fr * WP + 4 * c4 + 1;
-        d[0] = bf16_bits(v.x); d[1] = bf16_bits(v.y); d[2] = bf16_bits(v.z); d[3] = bf16_bits(v.w);
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * D3_THREADS) {      // four independent 16-byte loads in flight per thread
+        float4 v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * D3_THREADS;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[u] = -1;
+            if (i < nvec) {
+                const int c4 = i % W4, fr = i / W4, f = fr / 3, r = fr - f * 3;
+                const int ti = f - 1, yi = 2 * yo + r - 1;
+                dst[u] = fr * WP + 4 * c4 + 1;
+                if (ti >= 0 && ti < T && yi >= 0 && yi < H)
+                    v[u] = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * T + ti) * H + yi) * W) + c4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u] >= 0) {
+                unsigned short* d = xs + dst[u];
+                d[0] = bf16_bits(v[u].x); d[1] = bf16_bits(v[u].y); d[2] = bf16_bits(v[u].z); d[3] = bf16_bits(v[u].w);
+            }
     }
     for (int i = threadIdx.x; i < (T + 2) * 3; i += D3_THREADS) { xs[i * WP] = 0; xs[i * WP + W + 1] = 0; }
 }
@@ -186,15 +200,25 @@ __global__ void __launch_bounds__(D3_THREADS) d3d_first_bwd_w_mma_kernel(const _
     const uint32_t lm_addr = smem_u32(stage) + (8 * (lane >> 4) + (lane & 7)) * D3_STAGE_PITCH + ((lane >> 3) & 1) * 16;
 
     const int tiles_x = Wo >> 4, ntiles = T * tiles_x;
+    // gradient tile of (frame t, pixels x0 .. x0 + 15): 1 KB contiguous, two 16-byte pieces per lane; the next tile's pieces are
+    // requested before the current tile is consumed
+    auto tile_src = [&](int tile) {
+        const int t = tile / tiles_x, x0 = (tile - t * tiles_x) << 4;
+        return reinterpret_cast<const uint4*>(dpre + (((static_cast<size_t>(b) * T + t) * Ho + yo) * Wo + x0) * 32);
+    };
+    uint4 cur[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+    if (warp < ntiles) { const uint4* src = tile_src(warp); cur[0] = __ldg(src + lane); cur[1] = __ldg(src + lane + 32); }
     for (int tile = warp; tile < ntiles; tile += D3_WARPS) {
         const int t = tile / tiles_x, x0 = (tile - t * tiles_x) << 4;
-        const uint4* src = reinterpret_cast<const uint4*>(dpre + (((static_cast<size_t>(b) * T + t) * Ho + yo) * Wo + x0) * 32);
+        uint4 nxt[2] = {cur[0], cur[1]};
+        if (tile + D3_WARPS < ntiles) { const uint4* src = tile_src(tile + D3_WARPS); nxt[0] = __ldg(src + lane); nxt[1] = __ldg(src + lane + 32); }
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const int idx = lane + 32 * it;
-            *reinterpret_cast<uint4*>(stage + (idx >> 2) * D3_STAGE_PITCH + (idx & 3) * 16) = __ldg(src + idx);
+            *reinterpret_cast<uint4*>(stage + (idx >> 2) * D3_STAGE_PITCH + (idx & 3) * 16) = cur[it];
         }
+        cur[0] = nxt[0]; cur[1] = nxt[1];
         __syncwarp();
         uint32_t a[2][4];
         ldmatrix_x4_trans(a[0], lm_addr);                                    // channels 0..15

@@ -2,7 +2,11 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace p2i {
+
+constexpr int UPMOD_CPT_DEFAULT = 16;     // channels per thread of upmod_bwd_hi_kernel (measured: profiles/r2_upmod_ab.txt)
 
 // ------------------------------------------------------------------------------------------------
 // ConvsOut + tanh backward (p2igan.py:109-111):  dz = dout * (1 - out^2);
@@ -93,10 +97,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 //   dbias[c] += sum dpre ;  dpos[Y,X] = s*(1 - s/2) * sum_{b,c} dpre * up(z)
 // one thread per (pixel, 8 channels); a pixel's C/8 threads are consecutive.
 // ------------------------------------------------------------------------------------------------
-// Round 2: one thread per (pixel, 32 channels) instead of (pixel, 8 channels) -- the bilinear geometry, sigmoid(pos) and the index
-// arithmetic of a pixel are computed once per 32 channels (ncu on the 8-channel form: 47-66 % issue-slot utilisation at 35-43 %
-// occupancy, i.e. instruction-issue bound; 212 instructions per 8 channels, ~130 of them per-pixel overhead).
-__global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ pos,
+// NQ = 16-byte channel groups per thread (1, 2 or 4: 8 / 16 / 32 channels).  The bilinear geometry, sigmoid(pos) and the index
+// arithmetic of a pixel are computed once per thread, so more channels per thread means fewer instructions (ncu on the 8-channel
+// form: 47-66 % issue-slot utilisation, 212 instructions per 8 channels, ~130 of them per-pixel overhead) but also more registers
+// and fewer resident warps; the host picks NQ (P2I_UPMOD_CPT, profiles/r2_upmod_ab.txt).
+template <int NQ>
+__global__ void __launch_bounds__(256, NQ == 4 ? 2 : 3) upmod_bwd_hi_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ pos,
                                                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ dout,
                                                            __nv_bfloat16* __restrict__ gout, float* __restrict__ dbias,
                                                            float* __restrict__ dpos, int B, int h, int w, int C) {
@@ -104,14 +110,14 @@ __global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat1
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_db[i] = 0.f;
     __syncthreads();
     const int cg = C >> 3;                                      // 16-byte channel groups per pixel
-    const int cq = C >> 5;                                      // 32-channel quads per pixel (power of two: 2, 4, 8, 16)
+    const int cq = cg / NQ;                                     // threads per pixel (power of two <= 32, checked on the host)
     const int total = B * 4 * h * w * cq;                       // < 2^31 (checked on the host): 32-bit index arithmetic
     const int H2 = 2 * h, W2 = 2 * w;
     const float sy = (h > 1) ? static_cast<float>(h - 1) / static_cast<float>(H2 - 1) : 0.f;
     const float sx = (w > 1) ? static_cast<float>(w - 1) / static_cast<float>(W2 - 1) : 0.f;
-    float dbv[4][8];
+    float dbv[NQ][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NQ; ++a)
 #pragma unroll
         for (int k = 0; k < 8; ++k) dbv[a][k] = 0.f;
     // the trip count is warp-uniform (the ds reduction below shuffles with a full mask); lanes past the end carry ds = 0
@@ -132,21 +138,21 @@ __global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat1
         const float ly = fy - y0, lx = fx - x0;
         const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
         s = 2.f / (1.f + __expf(-pos[static_cast<size_t>(Y) * W2 + X]));
-        const uint4* zb = reinterpret_cast<const uint4*>(z + static_cast<size_t>(b) * h * w * C) + q4 * 4;
+        const uint4* zb = reinterpret_cast<const uint4*>(z + static_cast<size_t>(b) * h * w * C) + q4 * NQ;
         const uint4* za = zb + (static_cast<size_t>(y0) * w + x0) * cg;
         const uint4* zbq = zb + (static_cast<size_t>(y0) * w + x1) * cg;
         const uint4* zc = zb + (static_cast<size_t>(y1) * w + x0) * cg;
         const uint4* zd = zb + (static_cast<size_t>(y1) * w + x1) * cg;
-        const size_t o = static_cast<size_t>(pix) * cg + q4 * 4;
+        const size_t o = static_cast<size_t>(pix) * cg + q4 * NQ;
 #pragma unroll
-        for (int a4 = 0; a4 < 4; ++a4) {
+        for (int a4 = 0; a4 < NQ; ++a4) {
             const uint4 a = __ldg(za + a4), bq = __ldg(zbq + a4), c = __ldg(zc + a4), d = __ldg(zd + a4);
             const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
             const uint32_t cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
             const uint4 gq = __ldg(reinterpret_cast<const uint4*>(dout) + o + a4);
             const uint32_t gv[4] = {gq.x, gq.y, gq.z, gq.w};
-            const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * 4 + a4) * 2);
-            const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * 4 + a4) * 2 + 1);
+            const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * NQ + a4) * 2);
+            const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias) + (q4 * NQ + a4) * 2 + 1);
             const float bb[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
             uint32_t ov[4];
 #pragma unroll
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat1
                 const float d0 = (fmaf(s, u0, bb[2 * i]) > 0.f) ? gg.x : 0.f;
                 const float d1 = (fmaf(s, u1, bb[2 * i + 1]) > 0.f) ? gg.y : 0.f;
                 ds += d0 * u0 + d1 * u1;
-                dbv[a4][2 * i] += d0;  // the thread keeps its channel quad for the whole loop (stride % cq == 0)
+                dbv[a4][2 * i] += d0;  // the thread keeps its channel slice for the whole loop (stride % cq == 0)
                 dbv[a4][2 * i + 1] += d1;
                 ov[i] = pack_bf16x2(s * d0, s * d1);
             }
@@ -175,16 +181,16 @@ __global__ void __launch_bounds__(256, 2) upmod_bwd_hi_kernel(const __nv_bfloat1
         const int q4 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) & (cq - 1));
         for (int off = 16; off >= cq; off >>= 1) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NQ; ++a)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) dbv[a][k] += __shfl_xor_sync(0xffffffffu, dbv[a][k], off);
         }
         if ((threadIdx.x & 31) < cq) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < NQ; ++a)
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (dbv[a][k] != 0.f) atomicAdd(&s_db[(q4 * 4 + a) * 8 + k], dbv[a][k]);
+                    if (dbv[a][k] != 0.f) atomicAdd(&s_db[(q4 * NQ + a) * 8 + k], dbv[a][k]);
         }
     }
     __syncthreads();
@@ -596,11 +602,17 @@ extern "C" int p2i_upmod_bwd(const void* z, const float* pos, const float* bias,
     P2I_CHECK_ARG(z && pos && bias && dout && g_scratch && dz && dbias && dpos, "upmod_bwd: null pointer");
     P2I_CHECK_ARG(C % 64 == 0 && (C & (C - 1)) == 0 && C <= 1024, "upmod_bwd: C=%d must be a power of two in [64, 1024]", C);
     P2I_CHECK_ARG(static_cast<long long>(B) * 4 * h * w * (C / 8) < (1ll << 31), "upmod_bwd: tensor too large for 32-bit indexing");
-    const long long total = static_cast<long long>(B) * 4 * h * w * (C / 32);     // one thread per (pixel, 32 channels)
+    // channels per thread of the high-resolution pass: 8, 16 or 32 (P2I_UPMOD_CPT; read per call so that an A/B can switch it),
+    // raised until a pixel's threads fit one warp
+    int cpt = UPMOD_CPT_DEFAULT;
+    if (const char* e = getenv("P2I_UPMOD_CPT")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) cpt = v; }
+    while (C / cpt > 32) cpt *= 2;
+    const long long total = static_cast<long long>(B) * 4 * h * w * (C / cpt);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    // the grid-stride of upmod_bwd_hi must keep a thread on its channel quad: blocks * 256 is a multiple of C / 32 (a power of two <= 16)
-    upmod_bwd_hi_kernel<<<static_cast<unsigned>(blocks), 256, C * sizeof(float), as_stream(stream)>>>(
+    // the grid stride (blocks * 256) is a multiple of C / cpt, so a thread keeps its channel slice for its whole loop
+    const auto hi = cpt == 8 ? upmod_bwd_hi_kernel<1> : cpt == 16 ? upmod_bwd_hi_kernel<2> : upmod_bwd_hi_kernel<4>;
+    hi<<<static_cast<unsigned>(blocks), 256, C * sizeof(float), as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(z), pos, bias, static_cast<const __nv_bfloat16*>(dout),
         static_cast<__nv_bfloat16*>(g_scratch), dbias, dpos, B, h, w, C);
     P2I_CHECK_LAUNCH("upmod_bwd_hi_kernel");

@@ -14,7 +14,10 @@ for s in $steps; do
     guardb) # second changed kernel family, with a run-time switch back to the previous kernels
       timeout 300 python -m pytest tests -m gpu -q -rf -p no:cacheprovider --timeout 90 --timeout-method=thread -k "$P2I_GUARDSEL_B" > gpurun_out/${tag}_pytest_guardb.txt 2>&1; grc=$?
       echo "guardb rc=$grc" >> gpurun_out/${tag}_pytest_guardb.txt; tail -8 gpurun_out/${tag}_pytest_guardb.txt
-      if [ $grc -ne 0 ]; then export P2I_D3D_MMA=0; echo "GUARD B FAILED: P2I_D3D_MMA=0"; fi;;
+      if [ $grc -ne 0 ]; then export P2I_LIB_PATH=$PWD/p2i-gan-benchmark_b200/p2igan_b200/libp2i_sm100a_prev.so; echo "GUARD B FAILED: using $P2I_LIB_PATH"; fi;;
+    upsel) # pick the channels-per-thread variant of upmod_bwd_hi_kernel by measurement; the remaining steps run with it
+      timeout 200 python tools/bench_upmod.py gpurun_out/${tag}_upmod_best.txt > gpurun_out/${tag}_upmod_ab.txt 2>&1; echo "upsel rc=$?"; cat gpurun_out/${tag}_upmod_ab.txt | tail -6
+      if [ -s gpurun_out/${tag}_upmod_best.txt ]; then export P2I_UPMOD_CPT=$(cat gpurun_out/${tag}_upmod_best.txt); echo "P2I_UPMOD_CPT=$P2I_UPMOD_CPT"; fi;;
     tests) timeout 600 python -m pytest tests -m gpu -q -rf -p no:cacheprovider --timeout 120 --timeout-method=thread > gpurun_out/${tag}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.txt; tail -5 gpurun_out/${tag}_pytest.txt;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.txt; tail -3 gpurun_out/${tag}_smoke.txt;;
     bench) timeout 900 python bench.py > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "bench rc=$?"; head -c 600 gpurun_out/${tag}_bench_train.json;;
