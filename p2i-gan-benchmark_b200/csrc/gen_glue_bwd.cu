@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 // UPPos tail backward, pass 1 (high resolution): recompute pre = s*up(z)+bias,
 //   dpre = (pre > 0) ? dout : 0 ;  g = s * dpre (bf16, input of the transposed upsample)
 //   dbias[c] += sum dpre ;  dpos[Y,X] = s*(1 - s/2) * sum_{b,c} dpre * up(z)
-// one thread per (pixel, 8 channels); a pixel's C/8 threads are consecutive.
+// one thread per (pixel, 8 NQ channels); a pixel's threads are consecutive lanes of one warp.
 // ------------------------------------------------------------------------------------------------
 // NQ = 16-byte channel groups per thread (1, 2 or 4: 8 / 16 / 32 channels).  The bilinear geometry, sigmoid(pos) and the index
 // arithmetic of a pixel are computed once per thread, so more channels per thread means fewer instructions (ncu on the 8-channel

@@ -157,19 +157,25 @@ def bwd_w(dpre, x, B, T, H, W):
     return dW, db
 
 
-if __name__ == "__main__":
-    torch.manual_seed(0)
-    B, T, H, W = 2, 3, 8, 32
+def run(B=2, T=3, H=8, W=32, seed=0):
+    """-> (max |forward - torch|, max |dW - autograd|, max |db - autograd|, number of unwritten output slots)."""
+    torch.manual_seed(seed)
     x = torch.randn(B, T, H, W)
     w = torch.randn(32, 1, 3, 3, 3, requires_grad=True)
     bias = torch.randn(32, requires_grad=True)
     pre = F.conv3d(x[:, None], w, bias, stride=(1, 2, 2), padding=1)
-    ref = F.leaky_relu(pre, 0.2)                                             # [B, 32, T, Ho, Wo]
+    ref = F.leaky_relu(pre, 0.2).detach()                                    # [B, 32, T, Ho, Wo]
     y = fwd(x.numpy(), w.detach().reshape(32, 27).numpy(), bias.detach().numpy(), B, T, H, W)
     Ho, Wo = H // 2, W // 2
     y = torch.from_numpy(y).reshape(B, T, Ho // 2, Wo // 2, 2, 2, 32).permute(0, 6, 1, 2, 4, 3, 5).reshape(B, 32, T, Ho, Wo)
-    print("fwd max abs diff", float((y - ref).abs().max()), "nan", int(torch.isnan(y).sum()))
     dpre = torch.randn_like(pre)
     pre.backward(dpre)
     dW, db = bwd_w(dpre.permute(0, 2, 3, 4, 1).contiguous().numpy(), x.numpy(), B, T, H, W)
-    print("dW max abs diff", float(np.abs(dW - w.grad.reshape(32, 27).numpy()).max()), "db", float(np.abs(db - bias.grad.numpy()).max()))
+    return (float((y - ref).abs().max()), float(np.abs(dW - w.grad.reshape(32, 27).numpy()).max()),
+            float(np.abs(db - bias.grad.numpy()).max()), int(torch.isnan(y).sum()))
+
+
+if __name__ == "__main__":
+    e_fwd, e_dw, e_db, holes = run()
+    print("fwd max abs diff", e_fwd, "unwritten", holes)
+    print("dW max abs diff", e_dw, "db", e_db)

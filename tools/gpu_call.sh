@@ -44,6 +44,12 @@ for s in $steps; do
     graph) timeout 300 python tools/prof_graph.py gpurun_out/${tag}_graph_timeline.txt > gpurun_out/${tag}_graph_kernels.txt 2>&1; echo "graph rc=$?"; head -3 gpurun_out/${tag}_graph_kernels.txt;;
     convab) timeout 600 python tools/bench_conv.py > gpurun_out/${tag}_conv_ab.txt 2>&1; echo "convab rc=$?";;
     wgradab) timeout 600 python tools/bench_wgrad.py > gpurun_out/${tag}_wgrad_ab.txt 2>&1; echo "wgradab rc=$?";;
+    ncunew) # full capture of the kernels changed last (d3d.0 MMA kernels, UPPos backward) inside one training step; summary only travels back
+      timeout 200 ncu --set full --clock-control none --import-source on -k regex:"d3d_first|upmod_bwd" -s 24 -c 12 -o gpurun_out/${tag}_new_full \
+          python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_new.log 2>&1
+      echo "ncu new rc=$?"
+      ncu -i gpurun_out/${tag}_new_full.ncu-rep --page raw --csv > /tmp/new_raw.csv 2>/dev/null && python tools/ncu_summarize.py --glue /tmp/new_raw.csv gpurun_out/${tag}_new_full_summary.txt
+      mv gpurun_out/${tag}_new_full.ncu-rep /tmp/ 2>/dev/null; tail -14 gpurun_out/${tag}_new_full_summary.txt | cut -c1-200;;
     ncul)
       timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 420 --csv --log-file gpurun_out/${tag}_launches.csv \
           python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${tag}_ncu_list.log 2>&1

@@ -34,6 +34,8 @@ GLUE_KEYS = [
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
     ("smsp__inst_executed.sum", "inst"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%act"),
+    ("sm__inst_executed_pipe_tensor.sum", "inst_tensor"),
 ]
 if "--glue" in sys.argv:
     sys.argv.remove("--glue")
